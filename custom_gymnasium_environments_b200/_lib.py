@@ -1,0 +1,75 @@
+"""ctypes binding of libbeng.so -- the C ABI declared in include/beng.h.
+
+There is NO CPU fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from ._build import LIB_PATH
+
+_lib = None
+
+
+class SnakeParams(C.Structure):
+    _fields_ = [("grid_size", C.c_int32), ("max_steps", C.c_int32), ("autoreset_mode", C.c_int32),
+                ("reserved", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+
+
+class SnakeState(C.Structure):
+    _fields_ = [("core", C.c_void_p), ("ring", C.c_void_p)]
+
+
+class SnakeIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "obs", "reward", "terminated", "truncated", "score", "snake_length", "ep_return", "ep_length", "ep_score",
+        "done_count", "done_env", "done_count_next", "stats", "invalid_count")]
+
+
+# name -> (restype, argtypes); also the list of symbols include/beng.h declares (tests check it).
+SIGNATURES = {
+    "beng_version": (C.c_int, []),
+    "beng_compiled_arch": (C.c_int, []),
+    "beng_launch_count": (C.c_uint64, []),
+    "beng_fill_random_actions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint32, C.c_uint64,
+                                           C.c_uint64, C.c_void_p]),
+    "beng_snake_core_bytes": (C.c_size_t, [C.c_int64]),
+    "beng_snake_ring_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
+    "beng_snake_reset": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.POINTER(SnakeIO), C.c_void_p,
+                                   C.c_int64, C.c_int32, C.c_void_p]),
+    "beng_snake_step": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_void_p, C.POINTER(SnakeIO),
+                                  C.c_int64, C.c_void_p]),
+    "beng_snake_step_host": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_void_p, C.POINTER(SnakeIO),
+                                       C.c_int64] + [C.c_void_p] * 8),
+    "beng_snake_export_state": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_int64] +
+                                [C.c_void_p] * 10),
+}
+
+
+def library_path() -> str:
+    return LIB_PATH
+
+
+def load():
+    """Load libbeng.so (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the CUDA engine has not been built and there is no CPU fallback. "
+                "Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or custom_gymnasium_environments_b200._build.build_library()).")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        kind = {-1: "BENG_ERR_BAD_ARG", -2: "BENG_ERR_UNSUPPORTED"}.get(rc, f"cudaError {rc}")
+        raise RuntimeError(f"{what} failed: {kind}")

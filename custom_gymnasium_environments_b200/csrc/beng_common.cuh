@@ -1,0 +1,59 @@
+// Shared host/device helpers of libbeng: launch accounting, error mapping, PTX wrappers for the
+// bulk asynchronous copy engine (TMA, non-tensor form) used to drain observation tiles.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+
+#include "../../include/beng.h"
+
+namespace beng {
+
+extern std::atomic<uint64_t> g_launch_count;
+
+inline int finish_launch() {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+int device_sm_count();
+
+// ---- bulk async copy (cp.async.bulk, SASS UBLKCP) shared -> global -------------------------
+// One thread issues a contiguous copy of `bytes` (multiple of 16, both addresses 16-B aligned)
+// from this CTA's shared memory to global memory; completion is tracked per issuing thread in
+// bulk async-groups.
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Wait until at most N of this thread's bulk groups still have to READ their shared-memory source.
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// Wait until at most N of this thread's bulk groups are incomplete (writes performed).
+template <int N>
+__device__ __forceinline__ void bulk_wait() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+// Make generic-proxy writes to shared memory visible to the async proxy (the copy engine).
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// streaming (evict-first) 128-bit / 64-bit global loads for read-once inputs
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ long long ld_stream_s64(const long long *p) {
+    long long r;
+    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
+    return r;
+}
+
+}  // namespace beng

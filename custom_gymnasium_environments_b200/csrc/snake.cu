@@ -1,0 +1,519 @@
+// Batched SnakeEnvClassic for sm_100a: step + reward + termination + auto-reset + food RNG +
+// observation encoding in ONE kernel.
+//
+// Reference behaviour (paths relative to the reference root):
+//   SnakeEnvClassic.reset            snake_env_classic/snake_env.py:49-65
+//   SnakeEnvClassic.step             snake_env_classic/snake_env.py:67-119
+//   SnakeEnvClassic._place_food      snake_env_classic/snake_env.py:121-129
+//   SnakeEnvClassic._get_observation snake_env_classic/snake_env.py:131-143
+//
+// Design:
+//   * one THREAD per env does the integer dynamics out of a 16-byte state record (one LDG.128 /
+//     STG.128 per env, perfectly coalesced);
+//   * one CTA owns a TILE of T consecutive envs; their T x G*G observation bytes are contiguous in
+//     global memory, so the tile is composed in shared memory (zero fill, scatter body cells, food
+//     last) and drained with ONE bulk asynchronous copy (cp.async.bulk shared->global, the TMA
+//     engine, SASS UBLKCP) issued by a single thread -- no per-thread obs stores at all;
+//   * CTAs are persistent over tiles with a STAGES-deep ring of tile buffers, so the copy engine
+//     drains tile k while the threads compose tile k+1;
+//   * the shared-memory tile doubles as the O(1) occupancy map for self-collision and for the
+//     food rejection loop (the reference scans a Python list for both);
+//   * finished episodes are counted with warp votes, accumulated per CTA in shared memory and
+//     flushed with one set of global atomics per CTA; a warp-aggregated compaction emits the
+//     list of finished envs.
+//
+// The kernel is HBM-bound (450 algorithmic bytes per env-step, 400 of them the observation
+// write); there is nothing GEMM-shaped here and no tensor-core path is wanted.
+#include <climits>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#include "beng_common.cuh"
+#include "beng_rng.cuh"
+
+namespace beng {
+namespace {
+
+constexpr uint32_t FLAG_NEEDS_RESET = 1u;  // NEXT_STEP auto-reset bookkeeping
+constexpr int FOOD_NONE = 255;             // board full: no food on the grid (see place_food)
+
+// ---- 16-byte state record ---------------------------------------------------------------------
+struct Core {
+    int head_r, head_c, food_r, food_c;
+    int dir;
+    uint32_t flags;
+    int length, steps, ring_head;
+    uint32_t ctr;
+};
+
+__device__ __forceinline__ Core unpack(const uint4 v) {
+    Core s;
+    s.head_r = v.x & 0xFF;
+    s.head_c = (v.x >> 8) & 0xFF;
+    s.food_r = (v.x >> 16) & 0xFF;
+    s.food_c = (v.x >> 24) & 0xFF;
+    s.dir = v.y & 0xFF;
+    s.flags = (v.y >> 8) & 0xFF;
+    s.length = (v.y >> 16) & 0xFFFF;
+    s.steps = v.z & 0xFFFF;
+    s.ring_head = (v.z >> 16) & 0xFFFF;
+    s.ctr = v.w;
+    return s;
+}
+
+__device__ __forceinline__ uint4 pack(const Core &s) {
+    uint4 v;
+    v.x = (uint32_t)s.head_r | ((uint32_t)s.head_c << 8) | ((uint32_t)s.food_r << 16) | ((uint32_t)s.food_c << 24);
+    v.y = (uint32_t)s.dir | (s.flags << 8) | ((uint32_t)s.length << 16);
+    v.z = (uint32_t)s.steps | ((uint32_t)s.ring_head << 16);
+    v.w = s.ctr;
+    return v;
+}
+
+struct Args {
+    uint4 *core;
+    uint16_t *ring;
+    const long long *actions;  // step only
+    const uint8_t *mask;       // reset only (nullable)
+    beng_snake_io io;
+    long long n_envs;
+    uint64_t seed, env_id_base;
+    int G, max_steps, mode, first_call;
+};
+
+// _place_food (snake_env.py:121-129): draw (row, col) until the cell is not part of the snake.
+// `row` holds 1 for every body cell at this point (the food mark is written afterwards), so the
+// membership test is one shared-memory byte load.  The reference never returns when the board is
+// full (length == G*G, unreachable at G = 20 within 1000 steps); there the engine and the oracle
+// both leave the board without food instead of spinning.
+__device__ __forceinline__ void place_food(Core &s, EnvStream &rng, const uint8_t *row, int G) {
+    if (s.length >= G * G) {
+        s.food_r = s.food_c = FOOD_NONE;
+        return;
+    }
+    for (;;) {
+        const int r = rng.randint(0, G - 1);
+        const int c = rng.randint(0, G - 1);
+        if (row[r * G + c] == 0) {
+            s.food_r = r;
+            s.food_c = c;
+            return;
+        }
+    }
+}
+
+// reset (snake_env.py:49-65).  Expects `row` to be all zero.
+__device__ __forceinline__ void reset_env(Core &s, EnvStream &rng, uint8_t *row, uint16_t *ring, int G) {
+    const int center = G / 2;
+    s.head_r = s.head_c = center;
+    s.dir = 1;
+    s.length = 1;
+    s.steps = 0;
+    s.ring_head = 0;
+    s.flags = 0;
+    ring[0] = (uint16_t)(center * G + center);
+    row[center * G + center] = 1;
+    place_food(s, rng, row, G);
+}
+
+// Walk the body oldest -> newest, writing `mark` into the tile row.  Returns the tail cell and
+// reports whether `probe` is one of the body cells (`new_head in self.snake`, snake_env.py:93).
+__device__ __forceinline__ int scan_body(const Core &s, const uint16_t *ring, uint8_t *row, int cells, uint8_t mark,
+                                         int probe, bool &hit) {
+    int idx = s.ring_head - (s.length - 1);
+    if (idx < 0) idx += cells;
+    int tail = -1;
+    for (int i = 0; i < s.length; ++i) {
+        const int c = ring[idx];
+        if (i == 0) tail = c;
+        row[c] = mark;
+        hit |= (c == probe);
+        if (++idx == cells) idx = 0;
+    }
+    return tail;
+}
+
+template <int T, int STAGES, bool IS_RESET>
+__global__ void __launch_bounds__(T) snake_kernel(const Args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ long long s_stats[5];  // n_episodes, sum_return, sum_length, sum_score, max_score
+
+    const int tid = threadIdx.x;
+    const int G = a.G;
+    const int cells = G * G;
+    const int tile_bytes = T * cells;              // multiple of 16 because T is
+    const int tile_vec = tile_bytes >> 4;
+    const long long n_tiles = (a.n_envs + T - 1) / T;
+
+    if (tid < 5) s_stats[tid] = (tid == 4) ? LLONG_MIN : 0;
+    if (blockIdx.x == 0 && tid == 0 && a.io.done_count_next) *a.io.done_count_next = 0;  // for the NEXT step
+    // (ordered before first use by the __syncthreads inside the tile loop)
+
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        uint8_t *buf = smem + (size_t)(it % STAGES) * tile_bytes;
+        const long long env = tile * T + tid;
+        const bool active = env < a.n_envs;
+
+        // Issue this env's global loads first; their latency overlaps the wait + zero fill below.
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        long long act = 0;
+        bool selected = true;
+        if (active) {
+            raw = ld_stream_u4(a.core + env);
+            if constexpr (!IS_RESET) act = ld_stream_s64(a.actions + env);
+            else if (a.mask) selected = a.mask[env] != 0;
+        }
+
+        // The bulk copy that last used this buffer (tile it - STAGES) must have finished reading it.
+        if (it >= STAGES) {
+            if (tid == 0) bulk_wait_read<STAGES - 1>();
+        }
+        __syncthreads();
+
+        uint4 *buf16 = reinterpret_cast<uint4 *>(buf);
+        for (int i = tid; i < tile_vec; i += T) buf16[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+
+        // ---------------------------------------------------------------- per-env dynamics
+        bool ended = false;
+        int ep_ret = 0, ep_len = 0, ep_score = 0;
+        if (active) {
+            Core s = unpack(raw);
+            uint8_t *row = buf + tid * cells;
+            uint16_t *ring = a.ring + env * cells;
+            if constexpr (IS_RESET) {
+                if (selected && a.first_call) s.ctr = 0;
+            }
+            EnvStream rng(a.seed, a.env_id_base + (uint64_t)env, BENG_STREAM_ENV, s.ctr);
+            float rew = 0.0f;
+            int term = 0;
+
+            if constexpr (IS_RESET) {
+                if (selected) {
+                    reset_env(s, rng, row, ring, G);
+                } else {
+                    bool hit = false;
+                    scan_body(s, ring, row, cells, 1, -1, hit);
+                }
+            } else {
+                if (a.mode == BENG_AUTORESET_NEXT_STEP && (s.flags & FLAG_NEEDS_RESET)) {
+                    reset_env(s, rng, row, ring, G);  // action ignored, reward 0, not terminated
+                } else if (act < 0 || act > 3) {
+                    // The reference raises ValueError (snake_env.py:69-70); here the env is left
+                    // untouched and the event is counted for the host to raise on.
+                    if (a.io.invalid_count) atomicAdd(a.io.invalid_count, 1);
+                    bool hit = false;
+                    scan_body(s, ring, row, cells, 1, -1, hit);
+                } else {
+                    const int action = (int)act;
+                    int d = action - s.dir;
+                    if (d < 0) d = -d;
+                    if (d != 2) s.dir = action;  // reversal guard, snake_env.py:73-74
+                    // 0 up, 1 right, 2 down, 3 left in (row, col), snake_env.py:77-85
+                    const int nr = s.head_r + (s.dir == 2) - (s.dir == 0);
+                    const int nc = s.head_c + (s.dir == 1) - (s.dir == 3);
+                    const bool wall = (unsigned)nr >= (unsigned)G || (unsigned)nc >= (unsigned)G;  // :88-90
+                    const int new_cell = wall ? -1 : nr * G + nc;
+                    const int head_cell = s.head_r * G + s.head_c;
+                    const int food_cell = (s.food_r == FOOD_NONE) ? -2 : s.food_r * G + s.food_c;
+
+                    // A wall death under SAME_STEP returns the reset observation: the old body is
+                    // never drawn, so the row stays clean for reset_env below.
+                    const bool draw_body = !(wall && a.mode == BENG_AUTORESET_SAME_STEP);
+                    bool self_hit = false;
+                    int tail_cell = head_cell;
+                    if (draw_body) {
+                        if (s.length == 1) row[head_cell] = 1;
+                        else tail_cell = scan_body(s, ring, row, cells, 1, new_cell, self_hit);  // :93, tail included
+                    }
+                    const bool died = wall || self_hit;
+                    if (died) {
+                        rew = -10.0f;  // :90 / :94 -- nothing but `direction` was mutated
+                        term = 1;
+                    } else {
+                        if (++s.ring_head == cells) s.ring_head = 0;  // insert(0, new_head), :97
+                        ring[s.ring_head] = (uint16_t)new_cell;
+                        row[new_cell] = 1;
+                        s.head_r = nr;
+                        s.head_c = nc;
+                        if (new_cell == food_cell) {  // :101-104
+                            s.length += 1;
+                            rew = 10.0f;
+                            place_food(s, rng, row, G);
+                        } else {
+                            row[tail_cell] = 0;  // pop(), :107
+                        }
+                        s.steps = min(s.steps + 1, 65535);         // :109
+                        if (s.steps >= a.max_steps) term = 1;      // :112-114, reported as terminated
+                    }
+                    if (term && a.mode != BENG_AUTORESET_DISABLED) {
+                        ended = true;
+                        ep_score = s.length - 1;
+                        ep_ret = 10 * ep_score - (died ? 10 : 0);
+                        ep_len = s.steps + (died ? 1 : 0);  // the death step does not bump `steps`
+                        if (a.mode == BENG_AUTORESET_SAME_STEP) {
+                            if (draw_body) {  // un-draw the body so the row is clean again
+                                bool hit = false;
+                                if (!died) row[new_cell] = 0;
+                                Core old = s;
+                                if (!died) {  // the ring slot of the new head may still be in flight: skip it
+                                    old.ring_head = (s.ring_head == 0) ? cells - 1 : s.ring_head - 1;
+                                    old.length = s.length - 1;
+                                }
+                                if (old.length > 0) scan_body(old, ring, row, cells, 0, -1, hit);
+                            }
+                            reset_env(s, rng, row, ring, G);
+                        } else {
+                            s.flags |= FLAG_NEEDS_RESET;
+                        }
+                    }
+                }
+            }
+            if (s.food_r != FOOD_NONE) row[s.food_r * G + s.food_c] = 2;  // food written last, :139-141
+
+            s.ctr = rng.ctr;
+            a.core[env] = pack(s);
+            if constexpr (!IS_RESET) {
+                a.io.reward[env] = rew;
+                a.io.terminated[env] = (uint8_t)term;
+                if (a.io.truncated) a.io.truncated[env] = 0;  // never truncates, :119
+            }
+            if (a.io.score) a.io.score[env] = s.length - 1;
+            if (a.io.snake_length) a.io.snake_length[env] = s.length;
+            if (ended) {
+                if (a.io.ep_return) a.io.ep_return[env] = (float)ep_ret;
+                if (a.io.ep_length) a.io.ep_length[env] = ep_len;
+                if (a.io.ep_score) a.io.ep_score[env] = ep_score;
+            }
+        }
+
+        // ---------------------------------------------------------------- episode-done compaction + stats
+        if constexpr (!IS_RESET) {
+            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+            if (done_mask) {
+                const int lane = tid & 31;
+                if (a.io.done_env) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(a.io.done_count, (unsigned)__popc(done_mask));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    if (ended) a.io.done_env[base + __popc(done_mask & ((1u << lane) - 1u))] = (int)env;
+                }
+                if (a.io.stats) {
+                    const int n = __popc(done_mask);
+                    const int sr = __reduce_add_sync(0xFFFFFFFFu, ended ? ep_ret : 0);
+                    const int sl = __reduce_add_sync(0xFFFFFFFFu, ended ? ep_len : 0);
+                    const int ss = __reduce_add_sync(0xFFFFFFFFu, ended ? ep_score : 0);
+                    const int mx = __reduce_max_sync(0xFFFFFFFFu, ended ? ep_score : INT_MIN);
+                    if (lane == 0) {
+                        atomicAdd((unsigned long long *)&s_stats[0], (unsigned long long)n);
+                        atomicAdd((unsigned long long *)&s_stats[1], (unsigned long long)(long long)sr);
+                        atomicAdd((unsigned long long *)&s_stats[2], (unsigned long long)(long long)sl);
+                        atomicAdd((unsigned long long *)&s_stats[3], (unsigned long long)(long long)ss);
+                        atomicMax(&s_stats[4], (long long)mx);
+                    }
+                }
+            }
+        }
+
+        // ---------------------------------------------------------------- drain the tile
+        fence_proxy_async_smem();  // this thread's generic-proxy smem writes -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {
+            const long long first = tile * T;
+            const long long n_here = min((long long)T, a.n_envs - first);
+            const uint32_t bytes = (uint32_t)(n_here * cells);
+            const uint32_t bulk = bytes & ~15u;
+            if (bulk) bulk_store_s2g(a.io.obs + first * cells, buf, bulk);
+            bulk_commit();
+            for (uint32_t i = bulk; i < bytes; ++i) a.io.obs[first * cells + i] = (int8_t)buf[i];  // ragged last tile
+        }
+    }
+
+    if (tid == 0) bulk_wait<0>();  // all tiles written before the CTA (and its shared memory) retires
+    if constexpr (!IS_RESET) {
+        if (a.io.stats) {
+            __syncthreads();
+            if (tid < 4) {
+                if (s_stats[tid] != 0) atomicAdd((unsigned long long *)&a.io.stats[tid], (unsigned long long)s_stats[tid]);
+            } else if (tid == 4) {
+                if (s_stats[4] != LLONG_MIN) atomicMax((long long *)&a.io.stats[4], s_stats[4]);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) snake_export_kernel(const uint4 *__restrict__ core,
+                                                           const uint16_t *__restrict__ ring, long long n_envs, int G,
+                                                           int *head_r, int *head_c, int *food_r, int *food_c, int *dir,
+                                                           int *steps, int *length, uint32_t *ctr, int *body) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_envs) return;
+    const Core s = unpack(core[e]);
+    if (head_r) head_r[e] = s.head_r;
+    if (head_c) head_c[e] = s.head_c;
+    if (food_r) food_r[e] = (s.food_r == FOOD_NONE) ? -1 : s.food_r;
+    if (food_c) food_c[e] = (s.food_c == FOOD_NONE) ? -1 : s.food_c;
+    if (dir) dir[e] = s.dir;
+    if (steps) steps[e] = s.steps;
+    if (length) length[e] = s.length;
+    if (ctr) ctr[e] = s.ctr;
+    if (body) {
+        const int cells = G * G;
+        int idx = s.ring_head;
+        for (int i = 0; i < cells; ++i) {
+            body[e * cells + i] = (i < s.length) ? (int)ring[e * cells + idx] : -1;
+            if (--idx < 0) idx = cells - 1;
+        }
+    }
+}
+
+// ---- launch configuration ---------------------------------------------------------------------
+struct Config {
+    int tile;      // envs (= threads) per CTA tile
+    int stages;    // tile buffers per CTA
+    int ctas_per_sm;
+};
+
+// Tunable through BENG_SNAKE_CFG="tile,stages,ctas_per_sm" (read once; for profiling sweeps).
+Config pick_config(int G) {
+    static int env_tile = -1, env_stages = 0, env_ctas = 0;
+    if (env_tile < 0) {
+        env_tile = 0;
+        if (const char *e = getenv("BENG_SNAKE_CFG")) {
+            int t = 0, s = 0, c = 0;
+            if (sscanf(e, "%d,%d,%d", &t, &s, &c) == 3) { env_tile = t; env_stages = s; env_ctas = c; }
+        }
+    }
+    const int cells = G * G;
+    Config c{128, 2, 2};
+    if (env_tile > 0) c = Config{env_tile, env_stages, env_ctas};
+    const int budget = 200 * 1024;  // leave room for static smem and the 1 KB/CTA reservation
+    while (c.tile > 32 && (long long)c.tile * cells * c.stages * c.ctas_per_sm > budget) {
+        if (c.stages > 1 && (long long)c.tile * cells > 64 * 1024) c.stages = 1;
+        else c.tile >>= 1;
+    }
+    while (c.ctas_per_sm > 1 && (long long)c.tile * cells * c.stages * c.ctas_per_sm > budget) --c.ctas_per_sm;
+    if ((long long)c.tile * cells * c.stages > budget && c.stages > 1) c.stages = 1;
+    return c;
+}
+
+template <int T, int STAGES, bool IS_RESET>
+int launch_one(const Args &a, const Config &c, cudaStream_t stream) {
+    const size_t smem = (size_t)T * a.G * a.G * STAGES;
+    auto kern = snake_kernel<T, STAGES, IS_RESET>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long n_tiles = (a.n_envs + T - 1) / T;
+    long long grid = (long long)device_sm_count() * c.ctas_per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    kern<<<(unsigned)grid, T, smem, stream>>>(a);
+    return finish_launch();
+}
+
+template <bool IS_RESET>
+int launch(const Args &a, cudaStream_t stream) {
+    const Config c = pick_config(a.G);
+#define BENG_CASE(TT, SS) \
+    if (c.tile == TT && c.stages == SS) return launch_one<TT, SS, IS_RESET>(a, c, stream);
+    BENG_CASE(256, 1) BENG_CASE(256, 2) BENG_CASE(128, 1) BENG_CASE(128, 2) BENG_CASE(128, 3) BENG_CASE(64, 1)
+    BENG_CASE(64, 2) BENG_CASE(64, 3) BENG_CASE(64, 4) BENG_CASE(32, 1) BENG_CASE(32, 2) BENG_CASE(32, 4)
+#undef BENG_CASE
+    return BENG_ERR_UNSUPPORTED;
+}
+
+int check_common(const beng_snake_params *p, const beng_snake_state *st, const beng_snake_io *io, int64_t n_envs) {
+    if (!p || !st || !io || !st->core || !st->ring || !io->obs || n_envs < 0) return BENG_ERR_BAD_ARG;
+    if (p->grid_size < 2 || p->grid_size > 64) return BENG_ERR_UNSUPPORTED;
+    if (p->max_steps < 1 || p->max_steps > 65535) return BENG_ERR_UNSUPPORTED;
+    if (p->autoreset_mode < 0 || p->autoreset_mode > 2) return BENG_ERR_BAD_ARG;
+    if (((uintptr_t)st->core & 15) || ((uintptr_t)io->obs & 15)) return BENG_ERR_BAD_ARG;
+    if (io->done_env && !io->done_count) return BENG_ERR_BAD_ARG;
+    return 0;
+}
+
+Args make_args(const beng_snake_params *p, const beng_snake_state *st, const beng_snake_io *io, int64_t n_envs) {
+    Args a{};
+    a.core = (uint4 *)st->core;
+    a.ring = st->ring;
+    a.io = *io;
+    a.n_envs = n_envs;
+    a.seed = p->seed;
+    a.env_id_base = p->env_id_base;
+    a.G = p->grid_size;
+    a.max_steps = p->max_steps;
+    a.mode = p->autoreset_mode;
+    return a;
+}
+
+}  // namespace
+}  // namespace beng
+
+extern "C" {
+
+size_t beng_snake_core_bytes(int64_t n_envs) { return n_envs < 0 ? 0 : (size_t)n_envs * 16; }
+
+size_t beng_snake_ring_bytes(int64_t n_envs, int32_t grid_size) {
+    return (n_envs < 0 || grid_size < 1) ? 0 : (size_t)n_envs * (size_t)grid_size * grid_size * sizeof(uint16_t);
+}
+
+int beng_snake_reset(const beng_snake_params *p, const beng_snake_state *st, const beng_snake_io *io,
+                     const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream) {
+    if (int rc = beng::check_common(p, st, io, n_envs)) return rc;
+    if (n_envs == 0) return 0;
+    beng::Args a = beng::make_args(p, st, io, n_envs);
+    a.mask = mask_dev;
+    a.first_call = first_call;
+    return beng::launch<true>(a, (cudaStream_t)stream);
+}
+
+int beng_snake_step(const beng_snake_params *p, const beng_snake_state *st, const int64_t *actions_dev,
+                    const beng_snake_io *io, int64_t n_envs, void *stream) {
+    if (int rc = beng::check_common(p, st, io, n_envs)) return rc;
+    if (!actions_dev || !io->reward || !io->terminated) return BENG_ERR_BAD_ARG;
+    if (n_envs == 0) return 0;
+    beng::Args a = beng::make_args(p, st, io, n_envs);
+    a.actions = (const long long *)actions_dev;
+    return beng::launch<false>(a, (cudaStream_t)stream);
+}
+
+int beng_snake_step_host(const beng_snake_params *p, const beng_snake_state *st, int64_t *actions_dev,
+                         const beng_snake_io *io, int64_t n_envs, const int64_t *actions_host, int8_t *obs_host,
+                         float *reward_host, uint8_t *terminated_host, uint8_t *truncated_host, int32_t *score_host,
+                         int32_t *snake_length_host, void *stream) {
+    if (!actions_host || !actions_dev) return BENG_ERR_BAD_ARG;
+    if (int rc = beng::check_common(p, st, io, n_envs)) return rc;
+    if ((truncated_host && !io->truncated) || (score_host && !io->score) || (snake_length_host && !io->snake_length))
+        return BENG_ERR_BAD_ARG;
+    if (n_envs == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)n_envs, cells = (size_t)p->grid_size * p->grid_size;
+    cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    if (int rc = beng_snake_step(p, st, actions_dev, io, n_envs, stream)) return rc;
+#define BENG_D2H(dst, src, bytes) \
+    if (dst) { e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s); if (e != cudaSuccess) return (int)e; }
+    BENG_D2H(reward_host, io->reward, n * sizeof(float))
+    BENG_D2H(terminated_host, io->terminated, n)
+    BENG_D2H(truncated_host, io->truncated, n)
+    BENG_D2H(score_host, io->score, n * sizeof(int32_t))
+    BENG_D2H(snake_length_host, io->snake_length, n * sizeof(int32_t))
+    BENG_D2H(obs_host, io->obs, n * cells)
+#undef BENG_D2H
+    return 0;
+}
+
+int beng_snake_export_state(const beng_snake_params *p, const beng_snake_state *st, int64_t n_envs, int32_t *head_r,
+                            int32_t *head_c, int32_t *food_r, int32_t *food_c, int32_t *direction, int32_t *steps,
+                            int32_t *length, uint32_t *rng_counter, int32_t *body_cells_dev, void *stream) {
+    if (!p || !st || !st->core || !st->ring || n_envs < 0) return BENG_ERR_BAD_ARG;
+    if (n_envs == 0) return 0;
+    const unsigned blocks = (unsigned)((n_envs + 255) / 256);
+    beng::snake_export_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4 *)st->core, st->ring, (long long)n_envs, p->grid_size, head_r, head_c, food_r, food_c, direction,
+        steps, length, rng_counter, body_cells_dev);
+    return beng::finish_launch();
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+"""Shared host-side plumbing of the batched (VectorEnv-compatible) classes.
+
+`gymnasium.vector.VectorEnv` is duck-typed (gymnasium is not installed in this image): the
+batched classes expose num_envs, single_observation_space, single_action_space,
+observation_space, action_space, metadata["autoreset_mode"], reset(seed=, options=),
+step(actions), close().  When gymnasium IS importable they also subclass the real VectorEnv.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+try:  # pragma: no cover
+    from gymnasium.vector import VectorEnv as _VectorEnvBase  # type: ignore
+except Exception:
+    class _VectorEnvBase:  # minimal stand-in
+        metadata = {}
+        render_mode = None
+        closed = False
+
+        def close(self, **kwargs):
+            self.closed = True
+
+AUTORESET_MODES = {"disabled": 0, "next_step": 1, "same_step": 2}
+
+
+def _mode_name(mode) -> str:
+    name = getattr(mode, "value", mode)
+    name = str(name).lower()
+    if name not in AUTORESET_MODES:
+        raise ValueError(f"autoreset_mode must be one of {sorted(AUTORESET_MODES)}, got {mode!r}")
+    return name
+
+
+def require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("the batched engine runs on CUDA devices only (there is no CPU fallback)")
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA is not available: the batched engine has no CPU fallback")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def as_device_actions(actions, buf: torch.Tensor) -> torch.Tensor:
+    """Return a contiguous int64 CUDA tensor shaped like `buf` holding `actions` (zero-copy when possible)."""
+    if isinstance(actions, torch.Tensor):
+        if actions.device == buf.device and actions.dtype == torch.int64 and actions.is_contiguous() \
+                and actions.shape == buf.shape:
+            return actions
+        buf.copy_(actions.reshape(buf.shape), non_blocking=True)
+        return buf
+    arr = np.asarray(actions)
+    if arr.shape != tuple(buf.shape):
+        raise ValueError(f"actions must have shape {tuple(buf.shape)}, got {arr.shape}")
+    buf.copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)), non_blocking=False)
+    return buf

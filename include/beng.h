@@ -1,0 +1,148 @@
+/* beng.h -- C ABI of libbeng.so, the B200 (sm_100a) batched environment engine.
+ *
+ * This is the drop-in boundary for the step()/reset() hot path of the reference's Gymnasium
+ * environments.  The reference is pure Python and has no FFI of its own;
+ * the interface each entry point replaces is therefore a METHOD of the reference class, cited
+ * per function below (paths relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - return int = cudaError_t (0 == success) or BENG_ERR_* (negative) for argument errors.
+ *   - never allocate device memory, never synchronise, never throw: kernels are launched
+ *     asynchronously on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - every `*_dev` / state / io pointer is a DEVICE pointer to caller-owned memory, 16-byte
+ *     aligned, alive until the stream has drained.  The *_host entry points additionally take
+ *     (pinned) HOST buffers and enqueue the H2D/D2H copies around the kernel on the same stream.
+ *   - one host thread per GPU/process; env ids are GLOBAL (env_id_base + local index) so a given
+ *     env has the same trajectory however the batch is sharded over GPUs.
+ */
+#ifndef BENG_H
+#define BENG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BENG_VERSION 100 /* major*10000 + minor*100 + patch */
+
+enum {
+    BENG_ERR_BAD_ARG = -1,      /* NULL where a pointer is required, n_envs < 0, ... */
+    BENG_ERR_UNSUPPORTED = -2,  /* e.g. grid_size outside [2, 64] */
+};
+
+/* Auto-reset modes of the batched classes (gymnasium.vector.AutoresetMode names).  The reference
+ * has no auto-reset: DISABLED is exactly the reference class;
+ * SAME_STEP is the reference's caller loop `if terminated: env.reset()` folded into the step. */
+enum {
+    BENG_AUTORESET_DISABLED = 0,
+    BENG_AUTORESET_NEXT_STEP = 1,
+    BENG_AUTORESET_SAME_STEP = 2,
+};
+
+/* RNG streams of the counter-based generator (Philox4x32-10, csrc/beng_rng.cuh). */
+enum { BENG_STREAM_ENV = 0, BENG_STREAM_ACTION = 1 };
+
+/* Library version (BENG_VERSION of the build). */
+int beng_version(void);
+
+/* SM architecture the library was compiled for (100 for sm_100a). */
+int beng_compiled_arch(void);
+
+/* Number of kernel launches this process has issued through the library since load
+ * (bench.py reports it as `gpu_launches`). */
+uint64_t beng_launch_count(void);
+
+/* Synthetic uniform action tape on the device (bench / tests; stands in for a policy).
+ *   actions_dev[i * n_cols + c] = randint(0, n_choices - 1) drawn from u32 number
+ *   (step_index * n_cols + c) of stream BENG_STREAM_ACTION of env (env_id_base + i). */
+int beng_fill_random_actions(int64_t *actions_dev, int64_t n_envs, int32_t n_cols, int32_t n_choices,
+                             uint32_t step_index, uint64_t env_id_base, uint64_t seed, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * snake_env_classic  (reference: snake_env_classic/snake_env.py, class SnakeEnvClassic)
+ * ------------------------------------------------------------------------------------------ */
+
+/* Constructor arguments of SnakeEnvClassic (snake_env.py:19-47) plus the batching parameters. */
+typedef struct beng_snake_params {
+    int32_t grid_size;      /* `grid_size` ctor kwarg, default 20 (snake_env.py:19); 2..64 */
+    int32_t max_steps;      /* `self.max_steps = 1000` (snake_env.py:47); 1..65535 */
+    int32_t autoreset_mode; /* BENG_AUTORESET_* */
+    int32_t reserved;
+    uint64_t seed;          /* key of the counter-based stream */
+    uint64_t env_id_base;   /* global id of local env 0 */
+} beng_snake_params;
+
+/* Per-env state, structure-of-arrays in HBM.
+ *   core : n_envs x 16 B record {u8 head_r, head_c, food_r, food_c; u8 direction; u8 flags;
+ *          u16 length; u16 steps; u16 ring_head; u32 rng_counter}  -- one 128-bit load per env.
+ *          (`score` is not stored: score == length - 1 always, snake_env.py:57,102 vs :97,107.)
+ *   ring : n_envs x (grid_size^2) u16 body cells (r * G + c); newest at ring_head, oldest
+ *          (the tail) at ring_head - length + 1 (mod G^2).  Replaces the Python list
+ *          `self.snake` (snake_env.py:54,97,107). */
+typedef struct beng_snake_state {
+    void *core;     /* uint4[n_envs] */
+    uint16_t *ring; /* uint16_t[n_envs * grid_size * grid_size] */
+} beng_snake_state;
+
+/* Outputs of one batched step.  `obs`, `reward`, `terminated` are required; the rest may be NULL. */
+typedef struct beng_snake_io {
+    int8_t *obs;            /* [n_envs, G, G] 0 empty / 1 snake / 2 food  (_get_observation, snake_env.py:131-143) */
+    float *reward;          /* [n_envs] -10 / 0 / +10                       (snake_env.py:90,94,100,103) */
+    uint8_t *terminated;    /* [n_envs] death or steps >= max_steps        (snake_env.py:90,94,112-114) */
+    uint8_t *truncated;     /* [n_envs] always 0                           (snake_env.py:119) */
+    int32_t *score;         /* [n_envs] info["score"] after the step       (snake_env.py:117) */
+    int32_t *snake_length;  /* [n_envs] info["snake_length"]               (snake_env.py:117) */
+    /* written only for envs whose episode ended in this step (auto-reset modes): */
+    float *ep_return;       /* [n_envs] 10 * score - 10 * died */
+    int32_t *ep_length;     /* [n_envs] env steps in the episode (death step included) */
+    int32_t *ep_score;      /* [n_envs] */
+    /* warp-compacted list of the envs that finished this step (order unspecified): */
+    uint32_t *done_count;   /* [1]  must be zero when the step starts (see done_count_next) */
+    int32_t *done_env;      /* [n_envs] LOCAL env indices */
+    uint32_t *done_count_next; /* [1] nullable; zeroed BY this launch so it can serve as `done_count` of the
+                                  next step (ping-pong two counters: no memset launch between steps) */
+    /* running episode statistics, integer (exact, order independent):
+     * {n_episodes, sum_return, sum_length, sum_score, max_score} */
+    int64_t *stats;         /* [5] accumulated across steps; caller zeroes / all-reduces */
+    int32_t *invalid_count; /* [1] number of out-of-space actions seen (reference raises ValueError,
+                                   snake_env.py:69-70; here such an env is left untouched) */
+} beng_snake_io;
+
+/* Bytes the caller must allocate. */
+size_t beng_snake_core_bytes(int64_t n_envs);
+size_t beng_snake_ring_bytes(int64_t n_envs, int32_t grid_size);
+
+/* SnakeEnvClassic.reset (snake_env.py:49-65) for every env with mask[i] != 0 (mask NULL = all),
+ * then the observation / info of EVERY env is written to io (io->obs required; reward etc. untouched).
+ * `first_call` != 0 additionally zeroes rng_counter of the selected envs (constructor semantics). */
+int beng_snake_reset(const beng_snake_params *p, const beng_snake_state *st, const beng_snake_io *io,
+                     const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream);
+
+/* SnakeEnvClassic.step (snake_env.py:67-119) + _place_food (:121-129) + _get_observation (:131-143)
+ * + the auto-reset named in p->autoreset_mode, for all n_envs envs, in ONE kernel launch. */
+int beng_snake_step(const beng_snake_params *p, const beng_snake_state *st, const int64_t *actions_dev,
+                    const beng_snake_io *io, int64_t n_envs, void *stream);
+
+/* Same step with HOST action / result buffers (what a caller of the reference's numpy API holds):
+ * enqueues H2D(actions) -> kernel -> D2H(obs, reward, terminated[, truncated, score, snake_length])
+ * on `stream`.  Host pointers that are NULL are skipped (obs_host NULL keeps observations in HBM).
+ * Does not synchronise; the caller waits on the stream before reading the host buffers. */
+int beng_snake_step_host(const beng_snake_params *p, const beng_snake_state *st, int64_t *actions_dev,
+                         const beng_snake_io *io, int64_t n_envs, const int64_t *actions_host, int8_t *obs_host,
+                         float *reward_host, uint8_t *terminated_host, uint8_t *truncated_host, int32_t *score_host,
+                         int32_t *snake_length_host, void *stream);
+
+/* Unpack the SoA state into plain int32 arrays (tests, checkpoints, debugging).  Any output may be NULL.
+ * body_cells_dev, when given, is [n_envs, G*G] int32 filled head-first with r*G+c and -1 padding. */
+int beng_snake_export_state(const beng_snake_params *p, const beng_snake_state *st, int64_t n_envs, int32_t *head_r,
+                            int32_t *head_c, int32_t *food_r, int32_t *food_c, int32_t *direction, int32_t *steps,
+                            int32_t *length, uint32_t *rng_counter, int32_t *body_cells_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BENG_H */

@@ -1,0 +1,120 @@
+"""ctypes binding of the plain-C oracle (oracle/c/*.c -> oracle/_c/liboracle.so).
+
+TEST INFRASTRUCTURE.  `build()` compiles it with gcc; __graft_entry__.build() calls that so the
+prebuilt .so travels to the GPU box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_c", "liboracle.so")
+_lib = None
+
+AUTORESET = {"disabled": 0, "next_step": 1, "same_step": 2}
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, "c", f) for f in os.listdir(os.path.join(_HERE, "c")) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.run(["make", "-C", os.path.join(_HERE, "c")] + (["-B"] if force else []), check=True,
+                       capture_output=True)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.snake_oracle_create.restype = C.c_void_p
+        _lib.snake_oracle_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
+        _lib.snake_oracle_destroy.argtypes = [C.c_void_p]
+        _lib.snake_oracle_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _lib.snake_oracle_step.restype = C.c_int
+        _lib.snake_oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 10
+        _lib.snake_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        _lib.snake_oracle_get_body.restype = C.c_int
+        _lib.snake_oracle_get_body.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.snake_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.beng_oracle_draws_u32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        _lib.beng_oracle_action_tape.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_int,
+                                                 C.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def draws_u32(seed, env, stream, first, count):
+    out = np.empty(count, np.uint32)
+    lib().beng_oracle_draws_u32(seed, env, stream, first, count, _p(out))
+    return out
+
+
+def action_tape(seed, env_id_base, n_envs, step, n_choices, n_cols=1):
+    out = np.empty((n_envs, n_cols), np.int64)
+    lib().beng_oracle_action_tape(seed, env_id_base, n_envs, step, n_choices, n_cols, _p(out))
+    return out[:, 0] if n_cols == 1 else out
+
+
+class SnakeOracle:
+    """Batched CPU oracle with the same outputs as the device engine's snake step."""
+
+    def __init__(self, n_envs, grid_size=20, max_steps=1000, seed=0, env_id_base=0, autoreset="same_step"):
+        self.n, self.G = int(n_envs), int(grid_size)
+        self._h = C.c_void_p(lib().snake_oracle_create(self.n, self.G, max_steps, seed, env_id_base,
+                                                        AUTORESET[autoreset]))
+        n, G = self.n, self.G
+        self.obs = np.zeros((n, G, G), np.int8)
+        self.reward = np.zeros(n, np.float32)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+        self.score = np.zeros(n, np.int32)
+        self.length = np.zeros(n, np.int32)
+        self.ep_return = np.zeros(n, np.float32)
+        self.ep_length = np.zeros(n, np.int32)
+        self.ep_score = np.zeros(n, np.int32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().snake_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().snake_oracle_reset(self._h, _p(m), _p(self.obs), _p(self.score), _p(self.length))
+        return self.obs
+
+    def step(self, actions, want_obs=True):
+        a = np.ascontiguousarray(actions, np.int64)
+        assert a.shape == (self.n,)
+        self.invalid = lib().snake_oracle_step(
+            self._h, _p(a), _p(self.obs) if want_obs else None, _p(self.reward), _p(self.terminated),
+            _p(self.truncated), _p(self.score), _p(self.length), _p(self.ep_return), _p(self.ep_length),
+            _p(self.ep_score))
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    def state(self):
+        names = ["head_r", "head_c", "food_r", "food_c", "direction", "steps", "length"]
+        arrs = [np.zeros(self.n, np.int32) for _ in names]
+        ctr = np.zeros(self.n, np.uint32)
+        lib().snake_oracle_get_state(self._h, *[_p(a) for a in arrs], _p(ctr))
+        d = dict(zip(names, arrs))
+        d["rng_counter"] = ctr
+        return d
+
+    def body(self, env):
+        out = np.zeros(self.G * self.G + 1, np.int32)
+        n = lib().snake_oracle_get_body(self._h, env, _p(out))
+        return out[:n].copy()
+
+    def stats(self):
+        out = np.zeros(5, np.int64)
+        lib().snake_oracle_get_stats(self._h, _p(out))
+        return dict(zip(["n_episodes", "sum_return", "sum_length", "sum_score", "max_score"], out.tolist()))

@@ -1,0 +1,83 @@
+"""Import the UNMODIFIED reference modules from /root/reference (build container only).
+
+TEST INFRASTRUCTURE.  `/root/reference` does not exist on the GPU box; callers must check
+`reference_available()` and skip otherwise.  gymnasium / pygame are not installed in this
+image, so stub packages from oracle/refstubs/ are put on
+sys.path for the duration of the import only.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("BENG_REFERENCE_ROOT", "/root/reference")
+_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refstubs")
+_cache = {}
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "snake_env_classic", "snake_env.py"))
+
+
+def _stub_names():
+    names = []
+    for n in ("gymnasium", "pygame", "matplotlib"):
+        if importlib.util.find_spec(n) is None or n == "matplotlib":
+            names.append(n)
+    return names
+
+
+def _import_from(path: str, modname: str, extra_sys_path=()):
+    """Load file `path` as module `modname` with the stubs visible."""
+    if modname in _cache:
+        return _cache[modname]
+    saved_path = list(sys.path)
+    stubbed = {}
+    try:
+        sys.path[:0] = [_STUBS, *extra_sys_path]
+        for n in list(sys.modules):
+            root = n.split(".")[0]
+            if root in ("gymnasium", "pygame", "matplotlib") and root in _stub_names():
+                stubbed[n] = sys.modules.pop(n)
+        spec = importlib.util.spec_from_file_location(modname, path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        sys.path[:] = saved_path
+    _cache[modname] = mod
+    return mod
+
+
+def load_snake():
+    """-> the reference module snake_env_classic/snake_env.py (class SnakeEnvClassic)."""
+    return _import_from(os.path.join(REFERENCE_ROOT, "snake_env_classic", "snake_env.py"), "_ref_snake_env")
+
+
+def load_crypto():
+    """-> the reference module crypto_trading_env/crypto_trading_env.py."""
+    return _import_from(
+        os.path.join(REFERENCE_ROOT, "crypto_trading_env", "crypto_trading_env.py"), "_ref_crypto_trading_env"
+    )
+
+
+def load_traffic():
+    """-> (environment, utils) reference modules of traffic_management_env.
+
+    environment.py imports `config` and `utils` as TOP-LEVEL names (environment.py:16,23), so the
+    package directory itself goes on sys.path for the import and the two generic names are removed
+    from sys.modules afterwards (bus_system_env defines the same names; SURVEY.md section 2 note).
+    """
+    if "_ref_traffic_environment" in _cache:
+        return _cache["_ref_traffic_environment"], _cache["_ref_traffic_utils"]
+    d = os.path.join(REFERENCE_ROOT, "traffic_management_env")
+    for n in ("config", "utils"):
+        sys.modules.pop(n, None)
+    env_mod = _import_from(os.path.join(d, "environment.py"), "_ref_traffic_environment", extra_sys_path=(d,))
+    utils_mod = sys.modules.get("utils")
+    _cache["_ref_traffic_utils"] = utils_mod
+    for n in ("config", "utils"):
+        sys.modules.pop(n, None)
+    return env_mod, utils_mod

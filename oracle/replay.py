@@ -1,0 +1,65 @@
+"""ReplayRandom -- replays the engine's counter-based stream into the reference.
+
+TEST INFRASTRUCTURE.  The reference's hot-path envs call the module-level `random`
+(snake_env_classic/snake_env.py:4,125-126; crypto_trading_env/crypto_trading_env.py:13,135,...;
+traffic_management_env/environment.py:12 and utils.py:6) and `np.random.normal`
+(crypto_trading_env.py:148).  Rebinding those names to a ReplayRandom makes the reference
+consume exactly the u32 draws the device kernel consumes for env `env_id` (SURVEY.md
+section 0 fact 2), so trajectories can be compared bit for bit.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import philox
+
+
+class ReplayRandom:
+    """Duck-types the subset of `random` the reference uses, backed by draws_u32()."""
+
+    CHUNK = 4096
+
+    def __init__(self, seed: int, env_id: int, stream: int = philox.STREAM_ENV, start: int = 0):
+        self._seed = int(seed)
+        self._env = int(env_id)
+        self._stream = stream
+        self.counter = int(start)  # index of the next u32 draw == the kernel's per-env `ctr`
+        self._base = -1
+        self._buf = None
+
+    # -- raw stream -------------------------------------------------------
+    def _u32(self) -> int:
+        j = self.counter
+        base = j - (j % self.CHUNK)
+        if base != self._base:
+            self._buf = philox.draws_u32(self._seed, [self._env], base, self.CHUNK, self._stream)[0]
+            self._base = base
+        self.counter = j + 1
+        return int(self._buf[j - base])
+
+    # -- `random` module surface -------------------------------------------
+    def seed(self, *_a, **_k):
+        """No-op: the stream is positioned by (seed, env_id, counter), never reseeded."""
+
+    def randint(self, a: int, b: int) -> int:
+        return a + ((self._u32() * (b - a + 1)) >> 32)
+
+    def random(self) -> float:
+        a = self._u32() >> 5
+        b = self._u32() >> 6
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0)
+
+    def uniform(self, a: float, b: float) -> float:
+        return a + (b - a) * self.random()
+
+    def choice(self, seq):
+        return seq[self.randint(0, len(seq) - 1)]
+
+    # -- `np.random.normal` replacement -------------------------------------
+    def normal(self, loc: float = 0.0, scale: float = 1.0) -> float:
+        u1 = self.random()
+        u2 = self.random()
+        z = math.sqrt(-2.0 * math.log(1.0 - u1)) * math.cos(2.0 * math.pi * u2)
+        return loc + scale * z

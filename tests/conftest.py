@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+
+    return np.load(os.path.join(ROOT, "tests", "golden", "snake_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_cases(golden):
+    return [str(c) for c in golden["cases"]]
+
+
+def case_meta(golden, name):
+    G, n_envs, n_steps, seed, base, snap_every = (int(x) for x in golden[f"{name}/meta"])
+    return dict(G=G, n_envs=n_envs, n_steps=n_steps, seed=seed, base=base, snap_every=snap_every)
