@@ -324,7 +324,7 @@ def run_b200_arm(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(n), "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": SNAKE_BYTES_PER_ENV_STEP,
-                     "kernel": "beng::snake_kernel<128,2,false>", "kernel_ms": per_launch_ms},
+                     "kernel": "beng::snake_kernel<128,1,false,true>", "kernel_ms": per_launch_ms},
         "e2e": {"value": e2e_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
                 "steps": e2e_steps, "api": "BatchedSnakeEnv.step_host -> beng_snake_step_host (pinned host buffers, "
                                            "synchronous per step, full observation copied back)"},

@@ -263,7 +263,7 @@ def test_masked_reset_and_seed_rekey(pkg):
     assert (st1["steps"][::2] == 0).all() and (st1["steps"][1::2] == 5).all()
     assert torch.equal(st1["head_c"][1::2], st0["head_c"][1::2])
     assert (st1["rng_counter"][::2] > st0["rng_counter"][::2]).all()       # masked reset keeps drawing forward
-    assert bool(((obs == 1).sum(dim=(1, 2)) == 1).all())
+    assert bool(((obs == 1).sum(dim=(1, 2)) == st1["length"]).all()) and (st1["length"][::2] == 1).all()
     # re-keying with the same seed reproduces the constructor stream
     env.reset(seed=4)
     fresh = pkg.BatchedSnakeEnv(n, device=DEV, seed=4)
