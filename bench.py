@@ -314,6 +314,11 @@ def run_b200_arm(args):
         return
 
     peak, peak_src = load_peak()
+    import ctypes as C
+    t_, s_, c_ = C.c_int32(), C.c_int32(), C.c_int32()
+    lib.beng_snake_launch_config(20, n, C.byref(t_), C.byref(s_), C.byref(c_))
+    kernel_name = (f"beng::snake_kernel<T={t_.value},STAGES={s_.value},IS_RESET=false,OWNROW=true> "
+                   f"grid={c_.value} CTAs/SM persistent")
     per_launch_ms = ms / max(1, args.steps)  # rank-0 kernel time; the timed region is back-to-back step launches
     achieved = n * SNAKE_BYTES_PER_ENV_STEP / (per_launch_ms * 1e-3) / 1e9
     line = {
@@ -324,7 +329,7 @@ def run_b200_arm(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": load_traffic(n), "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": SNAKE_BYTES_PER_ENV_STEP,
-                     "kernel": "beng::snake_kernel<128,1,false,true>", "kernel_ms": per_launch_ms},
+                     "kernel": kernel_name, "kernel_ms": per_launch_ms},
         "e2e": {"value": e2e_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
                 "steps": e2e_steps, "api": "BatchedSnakeEnv.step_host -> beng_snake_step_host (pinned host buffers, "
                                            "synchronous per step, full observation copied back)"},

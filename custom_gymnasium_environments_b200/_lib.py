@@ -34,6 +34,8 @@ SIGNATURES = {
     "beng_launch_count": (C.c_uint64, []),
     "beng_fill_random_actions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_uint32, C.c_uint64,
                                            C.c_uint64, C.c_void_p]),
+    "beng_snake_launch_config": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32)]),
     "beng_snake_core_bytes": (C.c_size_t, [C.c_int64]),
     "beng_snake_ring_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "beng_snake_reset": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.POINTER(SnakeIO), C.c_void_p,

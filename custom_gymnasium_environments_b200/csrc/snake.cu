@@ -118,19 +118,31 @@ __device__ __forceinline__ void reset_env(Core &s, EnvStream &rng, uint8_t *row,
 
 // Walk the body oldest -> newest, writing `mark` into the tile row.  Returns the tail cell and
 // reports whether `probe` is one of the body cells (`new_head in self.snake`, snake_env.py:93).
-__device__ __forceinline__ int scan_body(const Core &s, const uint16_t *ring, uint8_t *row, int cells, uint8_t mark,
-                                         int probe, bool &hit) {
+// Only called for length >= 2.  `pre_tail` >= 0 is the tail entry fetched one tile ahead; the newest
+// entry always equals the head held in the state record, so a length-2 snake needs no ring load here.
+__device__ __forceinline__ int scan_body(const Core &s, const uint16_t *ring, uint8_t *row, int cells, int G,
+                                         uint8_t mark, int probe, bool &hit, int pre_tail = -1) {
     int idx = s.ring_head - (s.length - 1);
     if (idx < 0) idx += cells;
-    int tail = -1;
-    for (int i = 0; i < s.length; ++i) {
+    const int tail = (pre_tail >= 0) ? pre_tail : (int)ring[idx];
+    row[tail] = mark;
+    hit |= (tail == probe);
+    for (int i = 1; i < s.length - 1; ++i) {
+        if (++idx == cells) idx = 0;
         const int c = ring[idx];
-        if (i == 0) tail = c;
         row[c] = mark;
         hit |= (c == probe);
-        if (++idx == cells) idx = 0;
     }
+    const int head = s.head_r * G + s.head_c;
+    row[head] = mark;
+    hit |= (head == probe);
     return tail;
+}
+
+// Index of the tail entry in the ring (valid for length >= 2).
+__device__ __forceinline__ int tail_index(const Core &s, int cells) {
+    const int idx = s.ring_head - (s.length - 1);
+    return idx < 0 ? idx + cells : idx;
 }
 
 // Per-env inputs of one tile, loaded one tile ahead of their use (software pipeline).
@@ -144,7 +156,7 @@ struct Loaded {
 __device__ __forceinline__ void draw_body(const Core &s, const uint16_t *ring, uint8_t *row, int cells, int G) {
     bool hit = false;
     if (s.length == 1) row[s.head_r * G + s.head_c] = 1;
-    else if (s.length > 1) scan_body(s, ring, row, cells, 1, -1, hit);
+    else if (s.length > 1) scan_body(s, ring, row, cells, G, 1, -1, hit);
 }
 
 template <bool IS_RESET>
@@ -186,6 +198,13 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
     int pend_env = 0;
 
     Loaded cur = load_inputs<IS_RESET>(a, (long long)blockIdx.x * T + tid);
+    // tail ring entry of this thread's env, fetched one tile ahead (-1: not fetched / not needed)
+    int pre_tail = -1;
+    if constexpr (!IS_RESET) {
+        const long long env0 = (long long)blockIdx.x * T + tid;
+        const Core c0 = unpack(cur.raw);
+        if (env0 < a.n_envs && c0.length > 1) pre_tail = a.ring[env0 * cells + tail_index(c0, cells)];
+    }
     int it = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         uint8_t *buf = smem + (size_t)(it % STAGES) * tile_bytes;
@@ -266,7 +285,7 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
                     int tail_cell = head_cell;
                     if (draw) {
                         if (s.length == 1) row[head_cell] = 1;  // (a length-1 snake cannot hit itself)
-                        else tail_cell = scan_body(s, ring, row, cells, 1, new_cell, self_hit);  // :93, tail included
+                        else tail_cell = scan_body(s, ring, row, cells, G, 1, new_cell, self_hit, pre_tail);  // :93, tail included
                     }
                     const bool died = wall || self_hit;
                     if (died) {
@@ -302,15 +321,11 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
                         ep_len = s.steps + (died ? 1 : 0);  // the death step does not bump `steps`
                         if (a.mode == BENG_AUTORESET_SAME_STEP) {
                             if (draw) {  // un-draw the body so the row is clean again
+                                // Self-hit death: the body is unchanged.  Time limit: the body is the moved one
+                                // (new head in the state record, everything older in the ring).
                                 bool hit = false;
-                                Core old = s;
-                                if (!died) {  // new head: cleared directly; the older cells via the ring
-                                    row[new_cell] = 0;
-                                    old.ring_head = (s.ring_head == 0) ? cells - 1 : s.ring_head - 1;
-                                    old.length = s.length - 1;
-                                }
-                                if (died && old.length == 1) row[head_cell] = 0;
-                                else if (old.length > 0 && s.length > 1) scan_body(old, ring, row, cells, 0, -1, hit);
+                                if (s.length == 1) row[s.head_r * G + s.head_c] = 0;
+                                else scan_body(s, ring, row, cells, G, 0, -1, hit);
                             }
                             reset_env(s, rng, row, G);
                         } else {
@@ -379,6 +394,16 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
                 }
             }
         }
+        // Fetch the next tile's tail ring entry now (its state record, requested at the top of this iteration,
+        // has arrived by now) so that the dependent ring load is not exposed at the start of the next tile.
+        if constexpr (!IS_RESET) {
+            pre_tail = -1;
+            if (tile_next < n_tiles) {
+                const long long env_n = tile_next * T + tid;
+                const Core cn = unpack(nxt.raw);
+                if (env_n < a.n_envs && cn.length > 1) pre_tail = a.ring[env_n * cells + tail_index(cn, cells)];
+            }
+        }
         cur = nxt;
     }
 
@@ -436,8 +461,12 @@ struct Config {
     int ctas_per_sm;
 };
 
-// Tunable through BENG_SNAKE_CFG="tile,stages,ctas_per_sm" (read once; for profiling sweeps).
-Config pick_config(int G) {
+// Measured on B200 at 1M envs, G = 20 (profiles/snake_r1_sweep.txt): every single-stage shape that keeps
+// >= 2 CTAs resident per SM reaches the same ~11.5 G env-steps/s (the kernel is DRAM-bound), two-stage shapes
+// with fewer CTAs are ~15 % slower.  So: one tile buffer per CTA, as many CTAs per SM as shared memory
+// allows, and the largest tile that still gives every SM >= 2 tiles of work.
+// BENG_SNAKE_CFG="tile,stages,ctas_per_sm" overrides (read once; profiling sweeps).
+Config pick_config(int G, long long n_envs) {
     static int env_tile = -1, env_stages = 0, env_ctas = 0;
     if (env_tile < 0) {
         env_tile = 0;
@@ -446,16 +475,15 @@ Config pick_config(int G) {
             if (sscanf(e, "%d,%d,%d", &t, &s, &c) == 3) { env_tile = t; env_stages = s; env_ctas = c; }
         }
     }
-    const int cells = G * G;
-    Config c{128, 1, 3};
-    if (env_tile > 0) c = Config{env_tile, env_stages, env_ctas};
-    const int budget = 200 * 1024;  // leave room for static smem and the 1 KB/CTA reservation
-    while (c.tile > 32 && (long long)c.tile * cells * c.stages * c.ctas_per_sm > budget) {
-        if (c.stages > 1 && (long long)c.tile * cells > 64 * 1024) c.stages = 1;
-        else c.tile >>= 1;
-    }
-    while (c.ctas_per_sm > 1 && (long long)c.tile * cells * c.stages * c.ctas_per_sm > budget) --c.ctas_per_sm;
-    if ((long long)c.tile * cells * c.stages > budget && c.stages > 1) c.stages = 1;
+    const long long cells = (long long)G * G;
+    const long long budget = 200 * 1024;  // of 227 KB: leaves room for static smem + 1 KB/CTA reservation
+    if (env_tile > 0) return Config{env_tile, env_stages, env_ctas};
+    Config c{256, 1, 2};
+    const long long sms = device_sm_count();
+    while (c.tile > 32 && (c.tile * cells * 2 > budget || (n_envs + c.tile - 1) / c.tile < 2 * sms)) c.tile >>= 1;
+    c.ctas_per_sm = (int)(budget / (c.tile * cells));
+    if (c.ctas_per_sm < 1) c.ctas_per_sm = 1;
+    if (c.ctas_per_sm > 8) c.ctas_per_sm = 8;
     return c;
 }
 
@@ -474,7 +502,7 @@ int launch_one(const Args &a, const Config &c, cudaStream_t stream) {
 
 template <bool IS_RESET>
 int launch(const Args &a, cudaStream_t stream) {
-    const Config c = pick_config(a.G);
+    const Config c = pick_config(a.G, a.n_envs);
     const int cells = a.G * a.G;
     const bool ownrow = (cells % 16 == 0) && ((cells / 16) % 2 == 1) && !getenv("BENG_SNAKE_COOPZERO");
 #define BENG_CASE(TT, SS)                                                                   \
@@ -515,6 +543,15 @@ Args make_args(const beng_snake_params *p, const beng_snake_state *st, const ben
 }  // namespace beng
 
 extern "C" {
+
+int beng_snake_launch_config(int32_t grid_size, int64_t n_envs, int32_t *tile, int32_t *stages, int32_t *ctas_per_sm) {
+    if (grid_size < 2 || grid_size > 64 || n_envs < 0) return BENG_ERR_BAD_ARG;
+    const beng::Config c = beng::pick_config(grid_size, n_envs);
+    if (tile) *tile = c.tile;
+    if (stages) *stages = c.stages;
+    if (ctas_per_sm) *ctas_per_sm = c.ctas_per_sm;
+    return 0;
+}
 
 size_t beng_snake_core_bytes(int64_t n_envs) { return n_envs < 0 ? 0 : (size_t)n_envs * 16; }
 

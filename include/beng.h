@@ -112,6 +112,10 @@ typedef struct beng_snake_io {
                                    snake_env.py:69-70; here such an env is left untouched) */
 } beng_snake_io;
 
+/* Launch shape the step kernel uses for (grid_size, n_envs) on the current device: envs (= threads) per CTA
+ * tile, tile buffers per CTA, resident CTAs per SM.  Informational (bench.py names the kernel with it). */
+int beng_snake_launch_config(int32_t grid_size, int64_t n_envs, int32_t *tile, int32_t *stages, int32_t *ctas_per_sm);
+
 /* Bytes the caller must allocate. */
 size_t beng_snake_core_bytes(int64_t n_envs);
 size_t beng_snake_ring_bytes(int64_t n_envs, int32_t grid_size);
