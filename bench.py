@@ -223,6 +223,8 @@ def run_b200_arm(args):
     import custom_gymnasium_environments_b200 as pkg
     from custom_gymnasium_environments_b200.dist import all_reduce_episode_stats, init_process_group, summarize
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("BENG_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's banner goes to stdout and would precede the JSON line
     rank, local_rank, world = init_process_group()
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")

@@ -41,6 +41,14 @@ def lib():
         _lib.snake_oracle_get_body.restype = C.c_int
         _lib.snake_oracle_get_body.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _lib.snake_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.crypto_oracle_create.restype = C.c_void_p
+        _lib.crypto_oracle_create.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        _lib.crypto_oracle_destroy.argtypes = [C.c_void_p]
+        _lib.crypto_oracle_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.crypto_oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+        _lib.crypto_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        _lib.crypto_oracle_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        _lib.crypto_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib.beng_oracle_draws_u32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.beng_oracle_action_tape.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_int,
                                                  C.c_void_p]
@@ -118,3 +126,77 @@ class SnakeOracle:
         out = np.zeros(5, np.int64)
         lib().snake_oracle_get_stats(self._h, _p(out))
         return dict(zip(["n_episodes", "sum_return", "sum_length", "sum_score", "max_score"], out.tolist()))
+
+
+CRYPTO_DEFAULT_CFG = (10000.0, 0.001, 0.0005, 100.0, 100000.0, 0.02, 0.1)  # TradingConfig, crypto_trading_env.py:28-38
+CRYPTO_OBS_DIM = 261
+CRYPTO_HIST = 50
+
+
+class CryptoOracle:
+    """Batched CPU oracle (float64) with the same outputs as the device engine's crypto step."""
+
+    def __init__(self, n_envs, seed=0, env_id_base=0, autoreset="same_step", action_type="discrete",
+                 cfg=CRYPTO_DEFAULT_CFG, max_steps=1000):
+        self.n = int(n_envs)
+        self.continuous = action_type == "continuous"
+        cfg_arr = np.asarray(cfg, np.float64)
+        self._h = C.c_void_p(lib().crypto_oracle_create(self.n, seed, env_id_base, AUTORESET[autoreset],
+                                                         int(self.continuous), _p(cfg_arr), max_steps))
+        n = self.n
+        self.obs = np.zeros((n, CRYPTO_OBS_DIM), np.float32)
+        self.reward = np.zeros(n, np.float32)
+        self.reward64 = np.zeros(n, np.float64)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+        self.portfolio_value = np.zeros(n, np.float64)
+        self.current_price = np.zeros(n, np.float64)
+        self.trade_kind = np.zeros(n, np.uint8)
+        self.ep_return = np.zeros(n, np.float64)
+        self.ep_length = np.zeros(n, np.int32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().crypto_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().crypto_oracle_reset(self._h, _p(m), _p(self.obs))
+        return self.obs
+
+    def step(self, actions, want_obs=True):
+        if self.continuous:
+            a = np.ascontiguousarray(actions, np.float32)
+            assert a.shape == (self.n, 2)
+        else:
+            a = np.ascontiguousarray(actions, np.int64)
+            assert a.shape == (self.n,)
+        lib().crypto_oracle_step(self._h, _p(a), _p(self.obs) if want_obs else None, _p(self.reward),
+                                 _p(self.terminated), _p(self.truncated), _p(self.reward64),
+                                 _p(self.portfolio_value), _p(self.current_price), _p(self.trade_kind),
+                                 _p(self.ep_return), _p(self.ep_length))
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    def state(self, with_candles=False):
+        n = self.n
+        d = {"cash": np.zeros(n), "holdings": np.zeros(n), "trend_strength": np.zeros(n), "psychology": np.zeros(n),
+             "regime": np.zeros(n, np.int32), "step": np.zeros(n, np.int32), "rng_counter": np.zeros(n, np.uint32)}
+        candles = np.zeros((n, CRYPTO_HIST, 5)) if with_candles else None
+        lib().crypto_oracle_get_state(self._h, *[_p(d[k]) for k in ("cash", "holdings", "trend_strength",
+                                      "psychology", "regime", "step", "rng_counter")], _p(candles))
+        if with_candles:
+            d["candles"] = candles
+        return d
+
+    def set_state(self, d):
+        arrs = [np.ascontiguousarray(d[k], dt) for k, dt in (("cash", np.float64), ("holdings", np.float64),
+                ("trend_strength", np.float64), ("psychology", np.float64), ("regime", np.int32),
+                ("step", np.int32), ("rng_counter", np.uint32))]
+        candles = np.ascontiguousarray(d["candles"], np.float64) if "candles" in d else None
+        lib().crypto_oracle_set_state(self._h, *[_p(a) for a in arrs], _p(candles))
+
+    def stats(self):
+        out = np.zeros(4, np.float64)
+        lib().crypto_oracle_get_stats(self._h, _p(out))
+        return dict(zip(["n_episodes", "sum_return", "sum_length", "sum_final_value"], out.tolist()))

@@ -63,3 +63,24 @@ class ReplayRandom:
         u2 = self.random()
         z = math.sqrt(-2.0 * math.log(1.0 - u1)) * math.cos(2.0 * math.pi * u2)
         return loc + scale * z
+
+
+class NumpyWithReplayNormal:
+    """Stands in for the `np` name inside the reference crypto module: everything forwards to numpy except
+    `np.random.normal` (crypto_trading_env.py:148) and `np.random.seed` (:306), which go to the replay stream."""
+
+    class _Random:
+        def __init__(self, rr):
+            self._rr = rr
+
+        def normal(self, loc=0.0, scale=1.0):
+            return self._rr.normal(loc, scale)
+
+        def seed(self, *_a, **_k):
+            pass
+
+    def __init__(self, rr):
+        self.random = self._Random(rr)
+
+    def __getattr__(self, name):
+        return getattr(np, name)
