@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libbeng.so")
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared", "-DBENG_ARCH=100", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC", "-shared", "-DBENG_ARCH=100", "--expt-relaxed-constexpr", "--fmad=false",
 ]
 
 

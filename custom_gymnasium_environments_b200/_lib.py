@@ -27,6 +27,24 @@ class SnakeIO(C.Structure):
         "done_count", "done_env", "done_count_next", "stats", "invalid_count")]
 
 
+class CryptoParams(C.Structure):
+    _fields_ = [("initial_balance", C.c_double), ("trading_fee_rate", C.c_double), ("slippage_rate", C.c_double),
+                ("min_price", C.c_double), ("max_price", C.c_double), ("volatility_base", C.c_double),
+                ("market_psychology_factor", C.c_double), ("max_steps", C.c_int32), ("autoreset_mode", C.c_int32),
+                ("action_type", C.c_int32), ("window_head", C.c_int32), ("seed", C.c_uint64),
+                ("env_id_base", C.c_uint64)]
+
+
+class CryptoState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("scal", "meta", "ep_return", "close", "ohlv")]
+
+
+class CryptoIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "obs", "reward", "terminated", "truncated", "reward64", "portfolio_value", "current_price", "trade_kind",
+        "ep_return_out", "ep_length", "stats")]
+
+
 # name -> (restype, argtypes); also the list of symbols include/beng.h declares (tests check it).
 SIGNATURES = {
     "beng_version": (C.c_int, []),
@@ -44,6 +62,12 @@ SIGNATURES = {
                                   C.c_int64, C.c_void_p]),
     "beng_snake_step_host": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_void_p, C.POINTER(SnakeIO),
                                        C.c_int64] + [C.c_void_p] * 8),
+    "beng_crypto_reset": (C.c_int, [C.POINTER(CryptoParams), C.POINTER(CryptoState), C.POINTER(CryptoIO), C.c_void_p,
+                                    C.c_int64, C.c_int32, C.c_void_p]),
+    "beng_crypto_step": (C.c_int, [C.POINTER(CryptoParams), C.POINTER(CryptoState), C.c_void_p, C.POINTER(CryptoIO),
+                                   C.c_int64, C.c_void_p]),
+    "beng_crypto_step_host": (C.c_int, [C.POINTER(CryptoParams), C.POINTER(CryptoState), C.c_void_p,
+                                        C.POINTER(CryptoIO), C.c_int64] + [C.c_void_p] * 6),
     "beng_snake_export_state": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_int64] +
                                 [C.c_void_p] * 10),
 }

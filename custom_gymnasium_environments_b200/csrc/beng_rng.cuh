@@ -59,6 +59,11 @@ struct EnvStream {
         return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
     }
     __device__ __forceinline__ double uniform(double a, double b) { return a + (b - a) * random53(); }
+    // normal(mu, sd): Box-Muller on two random53() draws (four u32), the contract's np.random.normal stand-in
+    __device__ __forceinline__ double normal(double mu, double sd) {
+        const double u1 = random53(), u2 = random53();
+        return mu + sd * (sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2));
+    }
 };
 
 }  // namespace beng

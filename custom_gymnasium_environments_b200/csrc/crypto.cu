@@ -1,0 +1,488 @@
+// Batched CryptoTradingEnv for sm_100a: trade execution + regime-switching price walk + new candle +
+// termination + auto-reset + the 261-feature observation (OHLCV window, portfolio, RSI, MACD, Bollinger,
+// psychology) in ONE kernel.
+//
+// Reference behaviour (paths relative to the reference root, file crypto_trading_env/crypto_trading_env.py):
+//   TradingConfig :28-38                 TechnicalIndicators.{rsi,bollinger_bands,macd,_ema} :41-119
+//   MarketSimulator.generate_next_price :132-164, _update_market_regime :166-186, volatility :188-198,
+//                   trend :200-211, _update_market_psychology :213-221
+//   CryptoTradingEnv.reset :301-340, step :342-398, _execute_action :400-447, _execute_buy :449-476,
+//                   _execute_sell :478-503, _get_observation :505-561
+//
+// Design:
+//   * one THREAD per env; every state array is laid out [slot/field][env] so that a warp's accesses are
+//     contiguous (the 50-candle window is read as 250 fully coalesced loads per thread, high ILP);
+//   * the window is a ring over 50 slots with ONE head shared by all envs (params.window_head): a step
+//     overwrites the oldest slot, a reset rewrites all 50 slots in rotation -- heads never diverge between
+//     envs, so the layout stays coalesced whatever the episode boundaries are;
+//   * money, prices and indicators are float64 in the reference's operation order (the MACD is a difference
+//     of two EMAs of ~5e4-magnitude prices: float32 closes would break the 1e-5 tolerance); open/high/low/
+//     volume only feed the observation and are stored and normalised in float32;
+//   * the MACD signal line (an O(n^2) prefix loop in the reference, :94-100) is one forward scan;
+//   * the T x 261 float observation tile is contiguous in global memory: composed in shared memory (row
+//     stride 261 words = conflict-free) and drained with one bulk asynchronous copy (cp.async.bulk, UBLKCP).
+//
+// HBM-bound: ~2.4 KB per env-step (window read 1.2 KB + observation write 1.04 KB); no tensor-core work.
+#include <cfloat>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#include "beng_common.cuh"
+#include "beng_rng.cuh"
+
+namespace beng {
+namespace {
+
+constexpr int HIST = BENG_CRYPTO_HISTORY;
+constexpr int OBS = BENG_CRYPTO_OBS_DIM;
+constexpr uint32_t CFLAG_NEEDS_RESET = 1u;
+
+enum { BULL_RUN = 0, BEAR_MARKET = 1, SIDEWAYS = 2, CRASH = 3, RECOVERY = 4 };
+
+struct CArgs {
+    beng_crypto_params p;
+    beng_crypto_state st;
+    beng_crypto_io io;
+    const void *actions;
+    const uint8_t *mask;
+    long long n;
+    int first_call;
+};
+
+struct Market {
+    int regime;
+    double trend, psych;
+};
+
+__device__ __forceinline__ double vol_mult(int r) {  // :190-196
+    return r == BULL_RUN ? 1.2 : r == BEAR_MARKET ? 1.5 : r == SIDEWAYS ? 0.8 : r == CRASH ? 3.0 : 2.0;
+}
+__device__ __forceinline__ double base_trend(int r) {  // :202-208
+    return r == BULL_RUN ? 0.001 : r == BEAR_MARKET ? -0.001 : r == SIDEWAYS ? 0.0 : r == CRASH ? -0.005 : 0.002;
+}
+__device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// _update_market_regime, :166-186
+__device__ __forceinline__ void update_regime(Market &m, EnvStream &rng) {
+    const int pick = rng.randint(0, 1);  // random.choice of the two successors
+    int nr;
+    switch (m.regime) {
+        case BULL_RUN: nr = pick ? CRASH : SIDEWAYS; break;
+        case BEAR_MARKET: nr = pick ? RECOVERY : SIDEWAYS; break;
+        case SIDEWAYS: nr = pick ? BEAR_MARKET : BULL_RUN; break;
+        case CRASH: nr = pick ? BEAR_MARKET : RECOVERY; break;
+        default: nr = pick ? SIDEWAYS : BULL_RUN; break;
+    }
+    m.regime = nr;
+    if (nr == BULL_RUN || nr == RECOVERY) m.trend = rng.uniform(0.5, 1.0);
+    else if (nr == BEAR_MARKET || nr == CRASH) m.trend = rng.uniform(-1.0, -0.5);
+    else m.trend = rng.uniform(-0.2, 0.2);
+}
+
+// generate_next_price, :132-164, and _update_market_psychology, :213-221
+__device__ __forceinline__ double next_price(const beng_crypto_params &p, Market &m, EnvStream &rng, double cur,
+                                             double volume) {
+    if (rng.random53() < 0.01) update_regime(m, rng);
+    const double volatility = p.volatility_base * vol_mult(m.regime);
+    const double drift = (m.psych - 0.5) * p.market_psychology_factor;
+    const double trend = base_trend(m.regime) * m.trend;
+    const double eps = rng.normal(0.0, volatility);
+    const double volume_factor = 1.0 / (1.0 + volume * 0.1);
+    const double pct = (trend + drift + eps) * volume_factor;
+    const double np_ = clipd(cur * (1.0 + pct), p.min_price, p.max_price);
+    m.psych += pct * 10.0;
+    m.psych = clipd(m.psych, 0.0, 1.0);
+    m.psych += (0.5 - m.psych) * 0.01;
+    return np_;
+}
+
+__device__ __forceinline__ void store_candle(const CArgs &a, long long env, int slot, double open, double high,
+                                             double low, double close, double volume) {
+    a.st.close[(long long)slot * a.n + env] = close;
+    float *o = a.st.ohlv + ((long long)slot * 4) * a.n + env;
+    o[0] = (float)open;
+    o[a.n] = (float)high;
+    o[2 * a.n] = (float)low;
+    o[3 * a.n] = (float)volume;
+}
+
+// reset, :301-340: 50 warm-up candles from 50000.0; the newest lands in slot `head`.  Market state carries over.
+__device__ __noinline__ void warmup_window(const CArgs &a, Market &m, EnvStream &rng, long long env, int head) {
+    double price = 50000.0;
+    int slot = head + 1 == HIST ? 0 : head + 1;  // oldest
+    for (int k = 0; k < HIST; ++k) {
+        const double volume = rng.uniform(0.5, 2.0);
+        price = next_price(a.p, m, rng, price, volume);
+        const double high = price * rng.uniform(1.0, 1.02);
+        const double low = price * rng.uniform(0.98, 1.0);
+        const double open = price * rng.uniform(0.99, 1.01);
+        store_candle(a, env, slot, open, high, low, price, volume);
+        slot = slot + 1 == HIST ? 0 : slot + 1;
+    }
+}
+
+// NumPy's pairwise summation order for 8 <= n <= 128 (np.mean / np.std in the reference), n static.
+template <int N>
+__device__ __forceinline__ double np_sum(const double (&v)[N]) {
+    static_assert(N >= 8 && N < 24, "restated for the two sizes the reference uses (14, 20)");
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = v[j];
+    if (N >= 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += v[8 + j];
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int i = (N >= 16 ? 16 : 8); i < N; ++i) res += v[i];
+    return res;
+}
+
+// _get_observation, :505-561, into this env's shared-memory row.  `head` is the slot of the newest candle.
+__device__ __forceinline__ void compose_obs(const CArgs &a, long long env, int head, double cash, double holdings,
+                                            double psych, float *row) {
+    const long long n = a.n;
+    const double cur = a.st.close[(long long)head * n + env];
+    const double inv = 1.0 / cur;
+    const float inv_f = (float)inv;
+
+    const double mf = 2.0 / 13.0, ms = 2.0 / 27.0, mg = 2.0 / 10.0;  // _ema multipliers, :113
+    double ef = 0.0, es = 0.0, sig = 0.0, mx = 0.0, mn = 0.0;
+    double w[20];  // the last 20 closes (Bollinger window; its last 15 give the 14 RSI deltas)
+
+    int slot = head + 1 == HIST ? 0 : head + 1;  // oldest
+#pragma unroll
+    for (int k = 0; k < HIST; ++k) {
+        const double c = a.st.close[(long long)slot * n + env];
+        const float *o = a.st.ohlv + ((long long)slot * 4) * n + env;
+        const float fo = o[0], fh = o[n], fl = o[2 * n], fv = o[3 * n];
+        row[k * 5 + 0] = fo * inv_f;  // price_data / current_price, :513-515 (volume is divided too)
+        row[k * 5 + 1] = fh * inv_f;
+        row[k * 5 + 2] = fl * inv_f;
+        row[k * 5 + 3] = (float)(c * inv);
+        row[k * 5 + 4] = fv * inv_f;
+        if (k == 0) {
+            ef = es = mx = mn = c;  // _ema seeds at prices[0], :114
+        } else {
+            ef = (c * mf) + (ef * (1.0 - mf));  // :116-117
+            es = (c * ms) + (es * (1.0 - ms));
+            if (k == 25) sig = ef - es;                                    // macd_values[0] (prices[:26]), :94-98
+            else if (k > 25) sig = ((ef - es) * mg) + (sig * (1.0 - mg));  // _ema(macd_values, 9), :100
+            mx = c > mx ? c : mx;
+            mn = c < mn ? c : mn;
+        }
+        if (k >= HIST - 20) w[k - (HIST - 20)] = c;
+        slot = slot + 1 == HIST ? 0 : slot + 1;
+    }
+
+    const double value = cash + holdings * cur;  // :519-527
+    row[250] = (float)(cash / a.p.initial_balance);
+    row[251] = (float)(holdings * cur / a.p.initial_balance);
+    row[252] = (float)(value / a.p.initial_balance);
+
+    // RSI(14) over the last 14 deltas, :45-61
+    double g[14], l[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+        const double d = w[6 + i] - w[5 + i];
+        g[i] = d > 0 ? d : 0.0;
+        l[i] = d < 0 ? -d : 0.0;
+    }
+    const double avg_gain = np_sum(g) / 14.0, avg_loss = np_sum(l) / 14.0;
+    double rsi = 100.0;
+    if (avg_loss != 0) {
+        const double rs = avg_gain / avg_loss;
+        rsi = 100.0 - (100.0 / (1.0 + rs));
+    }
+    row[253] = (float)(rsi / 100.0);
+
+    // MACD(12, 26, 9) normalised by the close range, :538-547
+    const double macd_line = ef - es, hist = macd_line - sig, range = mx - mn;
+    if (range > 0) {
+        row[254] = (float)(macd_line / range);
+        row[255] = (float)(sig / range);
+        row[256] = (float)(hist / range);
+    } else {
+        row[254] = row[255] = row[256] = 0.0f;
+    }
+
+    // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
+    const double sma = np_sum(w) / 20.0;
+    double sq[20];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) {
+        const double d = w[i] - sma;
+        sq[i] = d * d;
+    }
+    const double sd = sqrt(np_sum(sq) / 20.0);
+    const double upper = sma + (2 * sd), lower = sma - (2 * sd);
+    row[257] = (float)((upper > lower) ? (cur - lower) / (upper - lower) : 0.5);
+    row[258] = (float)((sma > 0) ? (upper - lower) / sma : 0.0);
+    row[259] = (float)((sma > 0) ? (cur - sma) / sma : 0.0);
+    row[260] = (float)psych;  // :559
+}
+
+// _execute_buy, :449-476.  Returns 1 when the order executed.
+__device__ __forceinline__ int do_buy(const beng_crypto_params &p, EnvStream &rng, double &cash, double &holdings,
+                                      double amount, double price) {
+    if (amount <= 0 || cash < amount) return 0;
+    const double slippage = price * p.slippage_rate * rng.uniform(0.5, 1.5);
+    const double effective = price + slippage;
+    const double fee = amount * p.trading_fee_rate;
+    const double net = amount - fee;
+    cash -= amount;
+    holdings += net / effective;
+    return 1;
+}
+
+// _execute_sell, :478-503.  Returns 2 when the order executed.
+__device__ __forceinline__ int do_sell(const beng_crypto_params &p, EnvStream &rng, double &cash, double &holdings,
+                                       double crypto_amount, double price) {
+    if (crypto_amount <= 0 || holdings < crypto_amount) return 0;
+    const double slippage = price * p.slippage_rate * rng.uniform(0.5, 1.5);
+    const double effective = price - slippage;
+    const double received = crypto_amount * effective;
+    const double fee = received * p.trading_fee_rate;
+    holdings -= crypto_amount;
+    cash += received - fee;
+    return 2;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+template <int T, bool IS_RESET>
+__global__ void __launch_bounds__(T) crypto_kernel(const CArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *tile = reinterpret_cast<float *>(smem_raw);
+    const int tid = threadIdx.x;
+    const long long n = a.n;
+    const long long first = (long long)blockIdx.x * T;
+    const long long env = first + tid;
+    const bool active = env < n;
+    // slot that holds the newest candle once this call is done
+    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
+
+    bool ended = false;
+    double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
+    if (active) {
+        double cash = a.st.scal[env], holdings = a.st.scal[n + env];
+        Market m;
+        m.trend = a.st.scal[2 * n + env];
+        m.psych = a.st.scal[3 * n + env];
+        const uint32_t meta = a.st.meta[env];
+        int step = meta & 0xFFFF;
+        m.regime = (meta >> 16) & 0xFF;
+        uint32_t flags = meta >> 24;
+        uint32_t ctr = a.st.meta[n + env];
+        double ep_ret = a.st.ep_return[env];
+
+        bool selected = true;
+        if constexpr (IS_RESET) {
+            if (a.mask) selected = a.mask[env] != 0;
+            if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
+                m.regime = SIDEWAYS;
+                m.trend = 0.0;
+                m.psych = 0.5;
+                ctr = 0;
+            }
+        }
+        EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
+        double rew = 0.0, value = 0.0, price_out = 0.0;  // info values of THIS step (pre auto-reset)
+        int term = 0, trade = 0;
+
+        auto do_reset = [&]() {
+            cash = a.p.initial_balance;
+            holdings = 0.0;
+            step = 0;
+            flags = 0;
+            ep_ret = 0.0;
+            warmup_window(a, m, rng, env, head);
+        };
+
+        if constexpr (IS_RESET) {
+            if (selected) do_reset();
+        } else {
+            if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
+                // The ring head moved by one slot with this call: rewrite the whole window at the new rotation.
+                do_reset();
+                price_out = a.st.close[(long long)head * n + env];
+                value = cash + holdings * price_out;
+            } else {
+                // _execute_action, :400-447
+                const double price = a.st.close[(long long)a.p.window_head * n + env];
+                const double initial_value = cash + holdings * price;
+                if (a.p.action_type == 1) {
+                    const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
+                    const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
+                    const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
+                    if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
+                    else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
+                } else {
+                    const long long act = reinterpret_cast<const long long *>(a.actions)[env];
+                    if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
+                    else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
+                    else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
+                    else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
+                    // anything else is a hold: the reference does not validate (:424-436)
+                }
+                const double final_value = cash + holdings * price;
+                rew = final_value - initial_value;  // valued at the OLD price, :440-441
+                if (!trade) rew -= 1.0;             // :444-445
+                // next candle, :348-365
+                const double volume = rng.uniform(0.5, 2.0);
+                const double new_price = next_price(a.p, m, rng, price, volume);
+                const double high = new_price * rng.uniform(1.0, 1.02);
+                const double low = new_price * rng.uniform(0.98, 1.0);
+                store_candle(a, env, head, price, high, low, new_price, volume);
+                value = cash + holdings * new_price;
+                price_out = new_price;
+                step = min(step + 1, 65535);
+                term = (step >= a.p.max_steps) || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
+                ep_ret += rew;
+                if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
+                    ended = true;
+                    st_ret = ep_ret;
+                    st_len = (double)step;
+                    st_val = value;
+                    if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
+                    if (a.io.ep_length) a.io.ep_length[env] = step;
+                    if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
+                    else flags |= CFLAG_NEEDS_RESET;
+                }
+            }
+        }
+
+        compose_obs(a, env, head, cash, holdings, m.psych, tile + tid * OBS);
+
+        a.st.scal[env] = cash;
+        a.st.scal[n + env] = holdings;
+        a.st.scal[2 * n + env] = m.trend;
+        a.st.scal[3 * n + env] = m.psych;
+        a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
+        a.st.meta[n + env] = rng.ctr;
+        a.st.ep_return[env] = ep_ret;
+        if constexpr (!IS_RESET) {
+            a.io.reward[env] = (float)rew;
+            a.io.terminated[env] = (uint8_t)term;
+            if (a.io.truncated) a.io.truncated[env] = 0;
+            if (a.io.reward64) a.io.reward64[env] = rew;
+            if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
+            if (a.io.current_price) a.io.current_price[env] = price_out;
+            if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
+        }
+    }
+
+    // drain the observation tile with one bulk asynchronous copy
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        const long long n_here = min((long long)T, n - first);
+        const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
+        const uint32_t bulk = bytes & ~15u;
+        if (bulk) bulk_store_s2g(a.io.obs + first * OBS, tile, bulk);
+        bulk_commit();
+        for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[first * OBS + i] = tile[i];  // ragged last tile
+    }
+
+    if constexpr (!IS_RESET) {
+        if (a.io.stats) {
+            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+            if (done_mask) {  // rare: ~1 step in 1000
+                const double r = warp_sum(st_ret), l = warp_sum(st_len), v = warp_sum(st_val);
+                if ((tid & 31) == 0) {
+                    atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
+                    atomicAdd(&a.io.stats[1], r);
+                    atomicAdd(&a.io.stats[2], l);
+                    atomicAdd(&a.io.stats[3], v);
+                }
+            }
+        }
+    }
+    if (tid == 0) bulk_wait<0>();  // shared memory must outlive the copy
+}
+
+constexpr int CRYPTO_T = 64;  // envs (= threads) per CTA: 64 x 1044 B = 66.8 KB tile, 3 CTAs per SM
+
+template <bool IS_RESET>
+int launch(const CArgs &a, cudaStream_t stream) {
+    static int tile_env = -1;
+    if (tile_env < 0) {
+        tile_env = 0;
+        if (const char *e = getenv("BENG_CRYPTO_TILE")) tile_env = atoi(e);
+    }
+    const int T = tile_env > 0 ? tile_env : CRYPTO_T;
+#define BENG_CCASE(TT)                                                                                          \
+    if (T == TT) {                                                                                              \
+        const size_t smem = (size_t)TT * OBS * sizeof(float);                                                   \
+        auto kern = crypto_kernel<TT, IS_RESET>;                                                                \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e != cudaSuccess) return (int)e;                                                                    \
+        kern<<<(unsigned)((a.n + TT - 1) / TT), TT, smem, stream>>>(a);                                         \
+        return finish_launch();                                                                                 \
+    }
+    BENG_CCASE(32) BENG_CCASE(64) BENG_CCASE(96) BENG_CCASE(128) BENG_CCASE(192)
+#undef BENG_CCASE
+    return BENG_ERR_UNSUPPORTED;
+}
+
+int check(const beng_crypto_params *p, const beng_crypto_state *st, const beng_crypto_io *io, int64_t n) {
+    if (!p || !st || !io || n < 0) return BENG_ERR_BAD_ARG;
+    if (!st->scal || !st->meta || !st->ep_return || !st->close || !st->ohlv || !io->obs) return BENG_ERR_BAD_ARG;
+    if (((uintptr_t)io->obs & 15) || ((uintptr_t)st->close & 7)) return BENG_ERR_BAD_ARG;
+    if (p->window_head < 0 || p->window_head >= HIST) return BENG_ERR_BAD_ARG;
+    if (p->autoreset_mode < 0 || p->autoreset_mode > 2 || p->action_type < 0 || p->action_type > 1) return BENG_ERR_BAD_ARG;
+    if (p->max_steps < 1 || p->max_steps > 65535) return BENG_ERR_UNSUPPORTED;
+    return 0;
+}
+
+}  // namespace
+}  // namespace beng
+
+extern "C" {
+
+int beng_crypto_reset(const beng_crypto_params *p, const beng_crypto_state *st, const beng_crypto_io *io,
+                      const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream) {
+    if (int rc = beng::check(p, st, io, n_envs)) return rc;
+    if (n_envs == 0) return 0;
+    beng::CArgs a{*p, *st, *io, nullptr, mask_dev, (long long)n_envs, first_call};
+    return beng::launch<true>(a, (cudaStream_t)stream);
+}
+
+int beng_crypto_step(const beng_crypto_params *p, const beng_crypto_state *st, const void *actions_dev,
+                     const beng_crypto_io *io, int64_t n_envs, void *stream) {
+    if (int rc = beng::check(p, st, io, n_envs)) return rc;
+    if (!actions_dev || !io->reward || !io->terminated) return BENG_ERR_BAD_ARG;
+    if (n_envs == 0) return 0;
+    beng::CArgs a{*p, *st, *io, actions_dev, nullptr, (long long)n_envs, 0};
+    return beng::launch<false>(a, (cudaStream_t)stream);
+}
+
+int beng_crypto_step_host(const beng_crypto_params *p, const beng_crypto_state *st, void *actions_dev,
+                          const beng_crypto_io *io, int64_t n_envs, const void *actions_host, float *obs_host,
+                          float *reward_host, uint8_t *terminated_host, uint8_t *truncated_host, void *stream) {
+    if (!actions_host || !actions_dev) return BENG_ERR_BAD_ARG;
+    if (int rc = beng::check(p, st, io, n_envs)) return rc;
+    if (truncated_host && !io->truncated) return BENG_ERR_BAD_ARG;
+    if (n_envs == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)n_envs;
+    const size_t abytes = p->action_type == 1 ? n * 2 * sizeof(float) : n * sizeof(int64_t);
+    cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, abytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return (int)e;
+    if (int rc = beng_crypto_step(p, st, actions_dev, io, n_envs, stream)) return rc;
+#define BENG_D2H(dst, src, bytes) \
+    if (dst) { e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s); if (e != cudaSuccess) return (int)e; }
+    BENG_D2H(reward_host, io->reward, n * sizeof(float))
+    BENG_D2H(terminated_host, io->terminated, n)
+    BENG_D2H(truncated_host, io->truncated, n)
+    BENG_D2H(obs_host, io->obs, n * BENG_CRYPTO_OBS_DIM * sizeof(float))
+#undef BENG_D2H
+    return 0;
+}
+
+}  // extern "C"

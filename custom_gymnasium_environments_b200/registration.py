@@ -13,6 +13,8 @@ def register_all():
         return REGISTERED
     specs = [
         ("snake_env_classic-v0", "custom_gymnasium_environments_b200.snake:SnakeEnvClassic", 1000),
+        # crypto_trading_env/crypto_trading_env.py:739-743
+        ("CryptoTrading-v0", "custom_gymnasium_environments_b200.crypto:CryptoTradingEnv", 1000),
     ]
     for env_id, entry, max_steps in specs:
         if env_id not in registry:

@@ -146,6 +146,80 @@ int beng_snake_export_state(const beng_snake_params *p, const beng_snake_state *
                             int32_t *head_c, int32_t *food_r, int32_t *food_c, int32_t *direction, int32_t *steps,
                             int32_t *length, uint32_t *rng_counter, int32_t *body_cells_dev, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * crypto_trading_env  (reference: crypto_trading_env/crypto_trading_env.py, class CryptoTradingEnv)
+ * ------------------------------------------------------------------------------------------ */
+
+#define BENG_CRYPTO_HISTORY 50  /* TradingConfig.history_length (crypto_trading_env.py:33); fixed */
+#define BENG_CRYPTO_OBS_DIM 261 /* 50*5 + 3 + 8: what _get_observation really returns (:505-561); the declared
+                                   space says 260 (:285-286) -- SURVEY.md section 0 fact 7 */
+
+/* TradingConfig (crypto_trading_env.py:28-38) + episode limit (:298) + batching parameters. */
+typedef struct beng_crypto_params {
+    double initial_balance;          /* 10000.0 */
+    double trading_fee_rate;         /* 0.001 */
+    double slippage_rate;            /* 0.0005 */
+    double min_price;                /* 100.0 */
+    double max_price;                /* 100000.0 */
+    double volatility_base;          /* 0.02 */
+    double market_psychology_factor; /* 0.1 */
+    int32_t max_steps;               /* 1000 (:298) */
+    int32_t autoreset_mode;          /* BENG_AUTORESET_* */
+    int32_t action_type;             /* 0 = Discrete(5) int64[n]; 1 = Box(-1,1,(2,)) float32[n][2]  (:288-296) */
+    int32_t window_head;             /* slot (0..49) holding the NEWEST candle of every env before this call.
+                                        A step writes the new candle to (window_head+1)%50 -- the caller then
+                                        advances window_head by one; a reset leaves it unchanged. */
+    uint64_t seed;
+    uint64_t env_id_base;
+} beng_crypto_params;
+
+/* Per-env state, structure-of-arrays in HBM, env index fastest (coalesced for one thread per env).
+ * All money/price arithmetic is float64 like the reference; open/high/low/volume are observation-only
+ * features and are stored as float32. */
+typedef struct beng_crypto_state {
+    double *scal;      /* [4][n]  cash, holdings, trend_strength, market_psychology */
+    uint32_t *meta;    /* [2][n]  {step | regime << 16 | flags << 24}, rng_counter */
+    double *ep_return; /* [n]     running episode return */
+    double *close;     /* [50][n] close prices, ring over slots (see window_head) */
+    float *ohlv;       /* [50][4][n] open, high, low, volume */
+} beng_crypto_state;
+
+typedef struct beng_crypto_io {
+    float *obs;              /* [n][261]  _get_observation (:505-561) */
+    float *reward;           /* [n]       (:440-445) cast to float32 */
+    uint8_t *terminated;     /* [n]       step >= max_steps or value <= 0 or value >= 10 * initial (:382-386) */
+    uint8_t *truncated;      /* [n]       always 0 (:388) */
+    /* info dict (:390-398); all nullable */
+    double *reward64;        /* [n] the float64 reward */
+    double *portfolio_value; /* [n] */
+    double *current_price;   /* [n] */
+    uint8_t *trade_kind;     /* [n] 0 = no trade, 1 = buy, 2 = sell (info["trade_info"]["action"]) */
+    /* written only for envs whose episode ended in this step (auto-reset modes); nullable */
+    double *ep_return_out;   /* [n] */
+    int32_t *ep_length;      /* [n] */
+    double *stats;           /* [4] running {n_episodes, sum_return, sum_length, sum_final_value}; nullable */
+} beng_crypto_io;
+
+/* CryptoTradingEnv.reset (:301-340) for envs with mask[i] != 0 (NULL = all): 50 warm-up candles from 50000.0,
+ * cash/holdings/step reset, the MarketSimulator state is NOT reset.  first_call != 0 is the
+ * constructor: market state = (SIDEWAYS, 0.0, 0.5) (:125-130) and rng_counter = 0 for the selected envs.
+ * The observation of EVERY env is written to io->obs. */
+int beng_crypto_reset(const beng_crypto_params *p, const beng_crypto_state *st, const beng_crypto_io *io,
+                      const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream);
+
+/* CryptoTradingEnv.step (:342-398) + _execute_action/_execute_buy/_execute_sell (:400-503) +
+ * MarketSimulator.generate_next_price (:132-221) + _get_observation with all TechnicalIndicators (:41-119,
+ * :505-561) + auto-reset, for all envs, in ONE kernel launch.  `actions_dev` is int64[n] or float32[n][2]
+ * according to p->action_type. */
+int beng_crypto_step(const beng_crypto_params *p, const beng_crypto_state *st, const void *actions_dev,
+                     const beng_crypto_io *io, int64_t n_envs, void *stream);
+
+/* Same step with HOST action / result buffers: H2D(actions) -> kernel -> D2H(obs, reward, terminated) on `stream`.
+ * NULL host outputs are skipped.  Does not synchronise. */
+int beng_crypto_step_host(const beng_crypto_params *p, const beng_crypto_state *st, void *actions_dev,
+                          const beng_crypto_io *io, int64_t n_envs, const void *actions_host, float *obs_host,
+                          float *reward_host, uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
