@@ -1,16 +1,15 @@
 #!/usr/bin/env python
-"""Benchmark of the batched env-step hot path (BASELINE.json: env-steps/sec, batched SnakeEnv, 1M envs/GPU).
+"""Benchmark of the batched env-step hot path (BASELINE.json: env-steps/sec; headline = batched SnakeEnv, 1M envs/GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
-    python bench.py --impl reference [--gpus N] --steps K --warmup W   # CPU arm: the reference's step loop
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--env snake|crypto]   # this repo's CUDA engine
+    python bench.py --impl reference [--gpus N] --steps K --warmup W [--env …]  # CPU arm: the reference's step loop
 
-A "step" is ONE launch of the fused step kernel over the whole batch (1,048,576 envs per GPU), inputs
-resident in HBM; `value` = envs x steps x ranks / max-over-ranks device time (CUDA events).  `e2e` is the
-same metric through the host-buffer C-ABI call (`beng_snake_step_host`: pinned host actions in, numpy
-obs/reward/terminated out, copies inside the timed region).  `roofline` uses SURVEY.md 8(d)'s 450
-algorithmic bytes per env-step against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
-`cpu_baseline` times the pure-Python port of the reference's per-env step loop (oracle/snake_port.py; the
-reference itself cannot travel to the GPU box) on the host cores, on rank 0 at N=1 only.
+A "step" is ONE launch of the fused step kernel over the whole batch, inputs resident in HBM; `value` =
+envs x steps x ranks / max-over-ranks device time (CUDA events).  `e2e` is the same metric through the
+host-buffer C-ABI call (`beng_<env>_step_host`: pinned host actions in, numpy obs/reward/terminated out, copies
+inside the timed region).  `roofline` uses SURVEY.md 8(d)'s algorithmic bytes per env-step against the measured HBM
+copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times the pure-Python port of the reference's per-env step
+loop (oracle/*_port.py; the reference itself cannot travel to the GPU box) on the host cores, rank 0 at N=1 only.
 
 Prints exactly one JSON line on stdout (rank 0).
 """
@@ -31,58 +30,95 @@ if ROOT not in sys.path:
 
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
-SNAKE_BYTES_PER_ENV_STEP = 450  # obs 400 W + action 8 R + reward 4 W + flags 2 W + state 16 R/W + ring 2 R/W
-FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+class Workload:
+    """Per-env benchmark description (BASELINE.json configs[1..3])."""
+
+    def __init__(self, name, envs_per_gpu, bytes_per_env_step, n_choices, n_cols, dtype, label, obs_bytes,
+                 result_bytes, cpu_single_steps):
+        self.name, self.envs_per_gpu, self.bytes = name, envs_per_gpu, bytes_per_env_step
+        self.n_choices, self.n_cols, self.dtype, self.label = n_choices, n_cols, dtype, label
+        self.obs_bytes, self.result_bytes, self.cpu_single_steps = obs_bytes, result_bytes, cpu_single_steps
+
+
+WORKLOADS = {
+    # SURVEY.md 8(d): obs 400 W + action 8 R + reward 4 W + flags 2 W + state 16 R/W + ring 2 R/W
+    "snake": Workload("snake", 1 << 20, 450, 4, 1, "u8",
+                      "batched SnakeEnvClassic, G=20, random actions, SAME_STEP auto-reset (BASELINE.json configs[1])",
+                      400, 4 + 1 + 1 + 4 + 4, 20000),
+    # SURVEY.md 8(d): window read 1000 + candle 20 + obs 1044 W + action 8 + reward/flags 6 + scalars 112.
+    # (The "+408 if closes are kept in float64" is NOT added although they are: the lower figure is the
+    # conservative denominator.)
+    "crypto": Workload("crypto", 1 << 18, 2190, 5, 1, "f64",
+                       "batched CryptoTradingEnv, discrete actions, default TradingConfig, fp64 dynamics / fp32 obs, "
+                       "SAME_STEP auto-reset (BASELINE.json configs[2])", 1044, 4 + 1 + 1, 300),
+}
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's per-env Python step loop (port), one env per process
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker_loop(args):
-    """Step one SnakePort env with random actions and reset-on-done for `n_steps` steps (the loop shape of
-    crypto_trading_env/test_crypto_trading.py:410-416 applied to snake).  Returns (steps, seconds)."""
-    worker, n_steps = args
+    """Step one ported env with random actions and reset-on-done for `n_steps` steps (the loop shape of
+    crypto_trading_env/test_crypto_trading.py:410-416).  Returns (steps, seconds)."""
+    env_name, worker, n_steps = args
     import random
 
-    from oracle.snake_port import SnakePort
-
     rng = random.Random(1234 + worker)
-    env = SnakePort(20, rng=rng)
+    if env_name == "snake":
+        from oracle.snake_port import SnakePort
+
+        env, n_act = SnakePort(20, rng=rng), 4
+    else:
+        import numpy as np
+
+        from oracle.crypto_port import CryptoPort
+
+        np.random.seed(1234 + worker)
+        env, n_act = CryptoPort(action_type="discrete"), 5
     env.reset()
     randrange = rng.randrange
     t0 = time.perf_counter()
     for _ in range(n_steps):
-        _, _, term, trunc, _ = env.step(randrange(4))
+        _, _, term, trunc, _ = env.step(randrange(n_act))
         if term or trunc:
             env.reset()
     return n_steps, time.perf_counter() - t0
 
 
-def cpu_rate_single(seconds: float = 2.0) -> float:
-    n, dt = _cpu_worker_loop((0, 20000))
+def cpu_rate_single(env_name: str, seconds: float) -> float:
+    probe = WORKLOADS[env_name].cpu_single_steps
+    n, dt = _cpu_worker_loop((env_name, 0, probe))
     rate = n / dt
-    n, dt = _cpu_worker_loop((0, max(20000, int(rate * seconds))))
+    n, dt = _cpu_worker_loop((env_name, 0, max(probe, int(rate * seconds))))
     return n / dt
 
 
-def cpu_rate_parallel(pool, procs: int, steps_per_proc: int):
+def cpu_rate_parallel(pool, env_name: str, procs: int, steps_per_proc: int):
     t0 = time.perf_counter()
-    res = pool.map(_cpu_worker_loop, [(w, steps_per_proc) for w in range(procs)])
+    res = pool.map(_cpu_worker_loop, [(env_name, w, steps_per_proc) for w in range(procs)])
     wall = time.perf_counter() - t0
     return sum(r[0] for r in res) / wall, wall
 
 
-def c_oracle_rate(seconds: float = 1.5) -> float:
+def c_oracle_rate(env_name: str, seconds: float = 1.5) -> float:
     """Throughput of the plain-C oracle (1 thread), for context next to the Python port."""
     import numpy as np
 
-    from oracle.c_oracle import SnakeOracle
+    from oracle import c_oracle
 
-    n = 1 << 15
-    orc = SnakeOracle(n, seed=0)
-    orc.reset()
     rng = np.random.default_rng(0)
-    acts = rng.integers(0, 4, (16, n))
+    if env_name == "snake":
+        n = 1 << 15
+        orc = c_oracle.SnakeOracle(n, seed=0)
+        acts = rng.integers(0, 4, (16, n))
+    else:
+        n = 1 << 11
+        orc = c_oracle.CryptoOracle(n, seed=0)
+        acts = rng.integers(0, 5, (16, n))
+    orc.reset()
     orc.step(acts[0])
     t0 = time.perf_counter()
     k = 0
@@ -92,33 +128,40 @@ def c_oracle_rate(seconds: float = 1.5) -> float:
     return n * k / (time.perf_counter() - t0)
 
 
+def port_description(env_name, cores, per_proc):
+    what = {"snake": "SnakeEnvClassic (oracle/snake_port.py), G=20",
+            "crypto": "CryptoTradingEnv (oracle/crypto_port.py), discrete actions"}[env_name]
+    return (f"pure-Python port of {what}: 1 env per process x {cores} processes x {per_proc} random-action "
+            "steps with reset-on-done")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return  # rank 0 alone runs the CPU arm
+    w = WORKLOADS[args.env]
     cores = os.cpu_count() or 1
-    single = cpu_rate_single(1.0)
+    single = cpu_rate_single(args.env, 1.0)
     budget_s = 60.0
-    per_step = int(min(50000, max(200, single * budget_s / max(1, args.steps + args.warmup))))
+    per_step = int(min(50000, max(20, single * budget_s / max(1, args.steps + args.warmup))))
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_rate_parallel(pool, cores, per_step)
+            cpu_rate_parallel(pool, args.env, cores, per_step)
         t0 = time.perf_counter()
         total = 0
         for _ in range(args.steps):
-            res = pool.map(_cpu_worker_loop, [(w, per_step) for w in range(cores)])
+            res = pool.map(_cpu_worker_loop, [(args.env, k, per_step) for k in range(cores)])
             total += sum(r[0] for r in res)
         wall = time.perf_counter() - t0
     value = total / wall
-    sample = (f"pure-Python port of SnakeEnvClassic (oracle/snake_port.py), G=20, 1 env per process x {cores} "
-              f"processes, random actions, reset on done; each step = {per_step} env-steps per process")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
         "config": workload_config(args, per_gpu=args.envs_per_gpu),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": port_description(args.env, cores, per_step) + " per bench step",
                          "single_core_value": single},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -188,12 +231,14 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------
 def workload_config(args, per_gpu):
-    return {"workload": "batched SnakeEnvClassic, G=20, random actions, SAME_STEP auto-reset "
-                        "(BASELINE.json configs[1])",
-            "envs_per_gpu": per_gpu, "global_envs": per_gpu * args.gpus, "grid_size": 20, "max_steps": 1000,
-            "actions": "i.i.d. uniform{0..3} int64, device-generated tape (Philox stream 1), resident in HBM",
-            "l2_policy": "inputs larger than L2: each step streams 472 MB (400 MB obs write) through a 126 MB L2; "
-                         "action tape cycles over >= 64 distinct 8 MB tensors",
+    w = WORKLOADS[args.env]
+    mb = per_gpu * w.bytes / 1e6
+    return {"workload": w.label, "env": w.name,
+            "envs_per_gpu": per_gpu, "global_envs": per_gpu * args.gpus, "max_steps": 1000,
+            "actions": f"i.i.d. uniform{{0..{w.n_choices - 1}}} int64, device-generated tape (Philox stream 1), "
+                       "resident in HBM",
+            "l2_policy": f"inputs larger than L2: each step streams {mb:.0f} MB through a 126 MB L2; the action tape "
+                         "cycles over >= 64 distinct tensors",
             "parallelism": f"env-sharded x{args.gpus}, no data-path collective"}
 
 
@@ -206,25 +251,43 @@ def load_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic(n_envs):
+def load_traffic(env_name, n_envs):
     """Per-launch DRAM bytes of the step kernel from the committed ncu capture (profiles/), scaled to this batch."""
     try:
-        with open(os.path.join(ROOT, "profiles", "snake_step_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", f"{env_name}_step_traffic.json")) as f:
             d = json.load(f)
         return d["dram_bytes_per_env_step"] * n_envs
     except Exception:
         return None
 
 
+def make_env(pkg, env_name, n, dev, seed, base):
+    if env_name == "snake":
+        return pkg.BatchedSnakeEnv(n, 20, device=dev, seed=seed, env_id_base=base)
+    return pkg.BatchedCryptoTradingEnv(n, None, "discrete", device=dev, seed=seed, env_id_base=base)
+
+
+def kernel_description(lib, env_name, n):
+    import ctypes as C
+
+    if env_name == "snake":
+        t_, s_, c_ = C.c_int32(), C.c_int32(), C.c_int32()
+        lib.beng_snake_launch_config(20, n, C.byref(t_), C.byref(s_), C.byref(c_))
+        return (f"beng::snake_kernel<T={t_.value},STAGES={s_.value},IS_RESET=false,OWNROW=true>, "
+                f"{c_.value} persistent CTAs/SM")
+    return "beng::crypto_kernel<T=32,IS_RESET=false>: 128-thread warp-specialised CTA per 32-env tile (1 env warp + 3 window warps)"
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("BENG_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's banner goes to stdout and would precede the JSON line
+
     import custom_gymnasium_environments_b200 as pkg
     from custom_gymnasium_environments_b200.dist import all_reduce_episode_stats, init_process_group, summarize
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("BENG_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's banner goes to stdout and would precede the JSON line
     rank, local_rank, world = init_process_group()
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
@@ -233,11 +296,12 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = pkg._lib.load()
+    w = WORKLOADS[args.env]
     n = args.envs_per_gpu
     seed = 0
     base = rank * n  # contiguous global env-id slice per rank (weak scaling)
 
-    env = pkg.BatchedSnakeEnv(n, 20, device=dev, seed=seed, env_id_base=base)
+    env = make_env(pkg, args.env, n, dev, seed, base)
     env.reset()
     stream = torch.cuda.current_stream(dev)
 
@@ -245,8 +309,8 @@ def run_b200_arm(args):
     pool = max(64, min(args.steps + args.warmup, args.action_pool))
     tapes = torch.empty((pool, n), dtype=torch.int64, device=dev)
     for t in range(pool):
-        pkg._lib.check(lib.beng_fill_random_actions(tapes[t].data_ptr(), n, 1, 4, t, base, seed, stream.cuda_stream),
-                       "beng_fill_random_actions")
+        pkg._lib.check(lib.beng_fill_random_actions(tapes[t].data_ptr(), n, 1, w.n_choices, t, base, seed,
+                                                    stream.cuda_stream), "beng_fill_random_actions")
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -281,10 +345,9 @@ def run_b200_arm(args):
     # ---- end-to-end through the host-buffer C-ABI call -------------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     host_tapes = [tapes[t % pool].cpu().pin_memory() for t in range(min(e2e_steps + 2, 8))]
-    G = 20
     h2d = n * 8
-    d2h_full = n * (G * G + 4 + 1 + 1 + 4 + 4)
-    d2h_lite = n * (4 + 1 + 1 + 4 + 4)
+    d2h_full = n * (w.obs_bytes + w.result_bytes)
+    d2h_lite = n * w.result_bytes
 
     def time_e2e(copy_obs):
         for t in range(2):
@@ -306,8 +369,16 @@ def run_b200_arm(args):
     e2e_lite = time_e2e(False)
 
     # ---- episode statistics: the only collective, outside the step loop ---------------------------
-    stats = all_reduce_episode_stats(env.stats)
-    summary = summarize(stats)
+    if args.env == "snake":
+        stats = all_reduce_episode_stats(env.stats)
+        summary = summarize(stats)
+    else:
+        st = env.stats.clone()
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        v = st.tolist()
+        summary = {"episodes": int(v[0]), "episode_return_mean": v[1] / max(v[0], 1),
+                   "episode_len_mean": v[2] / max(v[0], 1), "final_value_mean": v[3] / max(v[0], 1)}
 
     if rank != 0:
         if world > 1:
@@ -316,25 +387,22 @@ def run_b200_arm(args):
         return
 
     peak, peak_src = load_peak()
-    import ctypes as C
-    t_, s_, c_ = C.c_int32(), C.c_int32(), C.c_int32()
-    lib.beng_snake_launch_config(20, n, C.byref(t_), C.byref(s_), C.byref(c_))
-    kernel_name = (f"beng::snake_kernel<T={t_.value},STAGES={s_.value},IS_RESET=false,OWNROW=true> "
-                   f"grid={c_.value} CTAs/SM persistent")
     per_launch_ms = ms / max(1, args.steps)  # rank-0 kernel time; the timed region is back-to-back step launches
-    achieved = n * SNAKE_BYTES_PER_ENV_STEP / (per_launch_ms * 1e-3) / 1e9
+    achieved = n * w.bytes / (per_launch_ms * 1e-3) / 1e9
+    api = {"snake": "BatchedSnakeEnv.step_host -> beng_snake_step_host",
+           "crypto": "BatchedCryptoTradingEnv.step_host -> beng_crypto_step_host"}[args.env]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
         "config": workload_config(args, per_gpu=n),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic(n), "peak_source": peak_src,
-                     "algorithmic_bytes_per_env_step": SNAKE_BYTES_PER_ENV_STEP,
-                     "kernel": kernel_name, "kernel_ms": per_launch_ms},
+                     "traffic": load_traffic(args.env, n), "peak_source": peak_src,
+                     "algorithmic_bytes_per_env_step": w.bytes,
+                     "kernel": kernel_description(lib, args.env, n), "kernel_ms": per_launch_ms},
         "e2e": {"value": e2e_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
-                "steps": e2e_steps, "api": "BatchedSnakeEnv.step_host -> beng_snake_step_host (pinned host buffers, "
-                                           "synchronous per step, full observation copied back)"},
+                "steps": e2e_steps, "api": api + " (pinned host buffers, synchronous per step, full observation "
+                                                 "copied back)"},
         "e2e_obs_on_device": {"value": e2e_lite, "unit": UNIT, "h2d_bytes_per_step": h2d,
                               "d2h_bytes_per_step": d2h_lite,
                               "note": "same call with obs_host=NULL: reward/terminated/info to host, observation "
@@ -345,16 +413,15 @@ def run_b200_arm(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        single = cpu_rate_single(2.0)
+        single = cpu_rate_single(args.env, 2.0)
         ctx = mp.get_context("fork")
         with ctx.Pool(cores) as pool_:
-            per_proc = int(single * 10.0)
-            par, wall = cpu_rate_parallel(pool_, cores, per_proc)
+            per_proc = max(20, int(single * 10.0))
+            par, wall = cpu_rate_parallel(pool_, args.env, cores, per_proc)
         line["cpu_baseline"] = {
             "value": par, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"pure-Python port of the reference step loop (oracle/snake_port.py): 1 env per process x "
-                      f"{cores} processes x {per_proc} random-action steps with reset-on-done ({wall:.1f} s wall)",
-            "single_core_value": single, "c_oracle_single_thread_value": c_oracle_rate()}
+            "sample": port_description(args.env, cores, per_proc) + f" ({wall:.1f} s wall)",
+            "single_core_value": single, "c_oracle_single_thread_value": c_oracle_rate(args.env)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -367,12 +434,16 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--env", choices=sorted(WORKLOADS), default="snake",
+                    help="snake = the BASELINE.json headline (configs[1]); crypto = configs[2]")
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--action-pool", type=int, default=256, help="distinct pre-generated action steps kept in HBM")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.envs_per_gpu is None:
+        args.envs_per_gpu = WORKLOADS[args.env].envs_per_gpu
     if args.impl == "reference":
         run_reference_arm(args)
     else:

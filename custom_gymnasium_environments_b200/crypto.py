@@ -43,6 +43,25 @@ class TradingConfig:
     market_psychology_factor: float = 0.1
 
 
+class _LazyInfos(dict):
+    """infos dict whose derived entries are computed on access (no per-step kernels for values nobody reads)."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.lazy = {}
+
+    def __missing__(self, key):
+        if key in self.lazy:
+            return self.lazy[key]()
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return super().__contains__(key) or key in self.lazy
+
+    def keys(self):
+        return list(super().keys()) + list(self.lazy)
+
+
 class BatchedCryptoTradingEnv(_VectorEnvBase):
     """N independent CryptoTradingEnv instances; state resident in HBM as [field][env] arrays."""
 
@@ -110,6 +129,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
                                  ptr(self.current_price), ptr(self.trade_kind), self.ep_return.data_ptr(),
                                  self.ep_length.data_ptr(), self.stats.data_ptr())
         self._host = None
+        self._info_cache = None
         self._needs_first_reset = True
 
     # ------------------------------------------------------------------ state views
@@ -152,13 +172,16 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
         return cand.permute(1, 0, 2).contiguous()
 
     def _infos(self):
-        info = {"cash": self.cash, "holdings": self.holdings, "market_regime": self.market_regime,
-                "market_psychology": self.market_psychology,
-                "episode": {"r": self.ep_return, "l": self.ep_length}, "_episode": self.terminated}
-        if self.portfolio_value is not None:
-            info.update(portfolio_value=self.portfolio_value, current_price=self.current_price,
-                        trade_kind=self.trade_kind, reward64=self.reward64)
-        return info
+        if self._info_cache is None:  # all entries are views of persistent buffers: build once
+            info = _LazyInfos({"cash": self.cash, "holdings": self.holdings,
+                               "market_psychology": self.market_psychology,
+                               "episode": {"r": self.ep_return, "l": self.ep_length}, "_episode": self.terminated})
+            info.lazy["market_regime"] = lambda: self.market_regime  # decoded from the packed state on access
+            if self.portfolio_value is not None:
+                info.update(portfolio_value=self.portfolio_value, current_price=self.current_price,
+                            trade_kind=self.trade_kind, reward64=self.reward64)
+            self._info_cache = info
+        return self._info_cache
 
     # ------------------------------------------------------------------ VectorEnv API
     def reset(self, *, seed=None, options=None):

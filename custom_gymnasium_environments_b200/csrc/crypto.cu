@@ -139,29 +139,21 @@ __device__ __forceinline__ double np_sum(const double (&v)[N]) {
     return res;
 }
 
-// _get_observation, :505-561, into this env's shared-memory row.  `head` is the slot of the newest candle.
-__device__ __forceinline__ void compose_obs(const CArgs &a, long long env, int head, double cash, double holdings,
-                                            double psych, float *row) {
-    const long long n = a.n;
-    const double cur = a.st.close[(long long)head * n + env];
+// Indicator part of _get_observation (:519-559) for one env, plus the normalised close column.
+// `closes` is the CTA's staging area [HIST-1][T] (float64, oldest first) holding the 49 older closes of every env
+// in the tile; `cur` is the newest close.  Writes row[k*5+3] for k < 49 and row[250..260].
+template <int T>
+__device__ __forceinline__ void compose_indicators(const beng_crypto_params &p, const double *closes, int lane_env,
+                                                   double cur, double cash, double holdings, double psych,
+                                                   float *row) {
     const double inv = 1.0 / cur;
-    const float inv_f = (float)inv;
-
     const double mf = 2.0 / 13.0, ms = 2.0 / 27.0, mg = 2.0 / 10.0;  // _ema multipliers, :113
     double ef = 0.0, es = 0.0, sig = 0.0, mx = 0.0, mn = 0.0;
     double w[20];  // the last 20 closes (Bollinger window; its last 15 give the 14 RSI deltas)
-
-    int slot = head + 1 == HIST ? 0 : head + 1;  // oldest
 #pragma unroll
     for (int k = 0; k < HIST; ++k) {
-        const double c = a.st.close[(long long)slot * n + env];
-        const float *o = a.st.ohlv + ((long long)slot * 4) * n + env;
-        const float fo = o[0], fh = o[n], fl = o[2 * n], fv = o[3 * n];
-        row[k * 5 + 0] = fo * inv_f;  // price_data / current_price, :513-515 (volume is divided too)
-        row[k * 5 + 1] = fh * inv_f;
-        row[k * 5 + 2] = fl * inv_f;
-        row[k * 5 + 3] = (float)(c * inv);
-        row[k * 5 + 4] = fv * inv_f;
+        const double c = (k == HIST - 1) ? cur : closes[k * T + lane_env];
+        if (k < HIST - 1) row[k * 5 + 3] = (float)(c * inv);  // close / current_price, :513-515
         if (k == 0) {
             ef = es = mx = mn = c;  // _ema seeds at prices[0], :114
         } else {
@@ -173,13 +165,12 @@ __device__ __forceinline__ void compose_obs(const CArgs &a, long long env, int h
             mn = c < mn ? c : mn;
         }
         if (k >= HIST - 20) w[k - (HIST - 20)] = c;
-        slot = slot + 1 == HIST ? 0 : slot + 1;
     }
 
     const double value = cash + holdings * cur;  // :519-527
-    row[250] = (float)(cash / a.p.initial_balance);
-    row[251] = (float)(holdings * cur / a.p.initial_balance);
-    row[252] = (float)(value / a.p.initial_balance);
+    row[250] = (float)(cash / p.initial_balance);
+    row[251] = (float)(holdings * cur / p.initial_balance);
+    row[252] = (float)(value / p.initial_balance);
 
     // RSI(14) over the last 14 deltas, :45-61
     double g[14], l[14];
@@ -223,6 +214,18 @@ __device__ __forceinline__ void compose_obs(const CArgs &a, long long env, int h
     row[260] = (float)psych;  // :559
 }
 
+// L2-coherent loads (bypass L1) for data another thread of this CTA may have just rewritten.
+__device__ __forceinline__ double ld_cg_f64(const double *p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ld_cg_f32(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
 // _execute_buy, :449-476.  Returns 1 when the order executed.
 __device__ __forceinline__ int do_buy(const beng_crypto_params &p, EnvStream &rng, double &cash, double &holdings,
                                       double amount, double price) {
@@ -255,131 +258,236 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Warp-specialised CTA over a tile of T consecutive envs, 4*T threads:
+//   threads [0, T)        "env" threads, one per env: trade, price walk, new candle, termination, auto-reset, then the
+//                         sequential indicator scans over the closes staged in shared memory;
+//   threads [T, 4T)       "window" threads: at kernel entry they fetch the 49 older candles of the whole tile with many
+//                         independent, fully coalesced loads (the memory-level parallelism of the kernel), stage the
+//                         closes in shared memory and, once the env threads have published 1/close_now, normalise
+//                         open/high/low/volume straight into the observation tile.
+// Two CTA barriers: (A) closes staged + 1/close published, (B) tile complete -> one bulk asynchronous store.
+// An env that auto-resets rewrites its whole window in this launch; it raises a flag and its elements are re-read
+// (L2-coherent) after barrier A.
 template <int T, bool IS_RESET>
-__global__ void __launch_bounds__(T) crypto_kernel(const CArgs a) {
+__global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
+    constexpr int NT = 4 * T, NW = 3 * T;  // threads, window threads
+    constexpr int OLD = HIST - 1;          // candles that exist before this step
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tile = reinterpret_cast<float *>(smem_raw);
+    float *tile = reinterpret_cast<float *>(smem_raw);                                    // [T][261]
+    double *s_close = reinterpret_cast<double *>(smem_raw + (size_t)T * OBS * sizeof(float));  // [49][T]
+    float *s_inv = reinterpret_cast<float *>(s_close + OLD * T);                          // [T]
+    uint8_t *s_reload = reinterpret_cast<uint8_t *>(s_inv + T);                            // [T]
+
     const int tid = threadIdx.x;
     const long long n = a.n;
     const long long first = (long long)blockIdx.x * T;
-    const long long env = first + tid;
-    const bool active = env < n;
     // slot that holds the newest candle once this call is done
     const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
+    const int oldest = head + 1 == HIST ? 0 : head + 1;  // slots oldest .. oldest+48 (mod 50) are the older candles
 
     bool ended = false;
     double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
-    if (active) {
-        double cash = a.st.scal[env], holdings = a.st.scal[n + env];
-        Market m;
-        m.trend = a.st.scal[2 * n + env];
-        m.psych = a.st.scal[3 * n + env];
-        const uint32_t meta = a.st.meta[env];
-        int step = meta & 0xFFFF;
-        m.regime = (meta >> 16) & 0xFF;
-        uint32_t flags = meta >> 24;
-        uint32_t ctr = a.st.meta[n + env];
-        double ep_ret = a.st.ep_return[env];
 
-        bool selected = true;
-        if constexpr (IS_RESET) {
-            if (a.mask) selected = a.mask[env] != 0;
-            if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
-                m.regime = SIDEWAYS;
-                m.trend = 0.0;
-                m.psych = 0.5;
-                ctr = 0;
-            }
-        }
-        EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
-        double rew = 0.0, value = 0.0, price_out = 0.0;  // info values of THIS step (pre auto-reset)
-        int term = 0, trade = 0;
-
-        auto do_reset = [&]() {
-            cash = a.p.initial_balance;
-            holdings = 0.0;
-            step = 0;
-            flags = 0;
-            ep_ret = 0.0;
-            warmup_window(a, m, rng, env, head);
-        };
-
-        if constexpr (IS_RESET) {
-            if (selected) do_reset();
-        } else {
-            if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
-                // The ring head moved by one slot with this call: rewrite the whole window at the new rotation.
-                do_reset();
-                price_out = a.st.close[(long long)head * n + env];
-                value = cash + holdings * price_out;
-            } else {
-                // _execute_action, :400-447
-                const double price = a.st.close[(long long)a.p.window_head * n + env];
-                const double initial_value = cash + holdings * price;
-                if (a.p.action_type == 1) {
-                    const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
-                    const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
-                    const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
-                    if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
-                    else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
-                } else {
-                    const long long act = reinterpret_cast<const long long *>(a.actions)[env];
-                    if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
-                    else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
-                    else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
-                    else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
-                    // anything else is a hold: the reference does not validate (:424-436)
-                }
-                const double final_value = cash + holdings * price;
-                rew = final_value - initial_value;  // valued at the OLD price, :440-441
-                if (!trade) rew -= 1.0;             // :444-445
-                // next candle, :348-365
-                const double volume = rng.uniform(0.5, 2.0);
-                const double new_price = next_price(a.p, m, rng, price, volume);
-                const double high = new_price * rng.uniform(1.0, 1.02);
-                const double low = new_price * rng.uniform(0.98, 1.0);
-                store_candle(a, env, head, price, high, low, new_price, volume);
-                value = cash + holdings * new_price;
-                price_out = new_price;
-                step = min(step + 1, 65535);
-                term = (step >= a.p.max_steps) || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
-                ep_ret += rew;
-                if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
-                    ended = true;
-                    st_ret = ep_ret;
-                    st_len = (double)step;
-                    st_val = value;
-                    if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
-                    if (a.io.ep_length) a.io.ep_length[env] = step;
-                    if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
-                    else flags |= CFLAG_NEEDS_RESET;
-                }
-            }
-        }
-
-        compose_obs(a, env, head, cash, holdings, m.psych, tile + tid * OBS);
-
-        a.st.scal[env] = cash;
-        a.st.scal[n + env] = holdings;
-        a.st.scal[2 * n + env] = m.trend;
-        a.st.scal[3 * n + env] = m.psych;
-        a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
-        a.st.meta[n + env] = rng.ctr;
-        a.st.ep_return[env] = ep_ret;
+    if (tid >= T) {
+        // ======================================================================== window threads
+        // Thread (q, e): env column e = j % T of the tile, slots k = q, q+3, q+6, ... (q = j / T in 0..2).  Per slot it
+        // fetches open/high/low/volume (held in registers) and the close (staged in shared memory); slot and field
+        // offsets are compile-time, so the address arithmetic is one pointer bump per value.
+        const int j = tid - T;
+        const int e = j % T, q = j / T;
+        constexpr int PER = (OLD + 2) / 3;  // 17 slots per thread
+        const bool col_ok = first + e < n;
+        const float *obase = a.st.ohlv + first + e;
+        const double *cbase = a.st.close + first + e;
+        float v[PER][4];
         if constexpr (!IS_RESET) {
-            a.io.reward[env] = (float)rew;
-            a.io.terminated[env] = (uint8_t)term;
-            if (a.io.truncated) a.io.truncated[env] = 0;
-            if (a.io.reward64) a.io.reward64[env] = rew;
-            if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
-            if (a.io.current_price) a.io.current_price[env] = price_out;
-            if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int k = q + 3 * i;
+                if (k < OLD && col_ok) {
+                    int slot = oldest + k;
+                    slot = slot >= HIST ? slot - HIST : slot;
+                    const float *o = obase + (long long)slot * 4 * n;
+                    v[i][0] = o[0];
+                    v[i][1] = o[n];
+                    v[i][2] = o[2 * n];
+                    v[i][3] = o[3 * n];
+                    s_close[k * T + e] = cbase[(long long)slot * n];
+                }
+            }
+        }
+        __syncthreads();  // (A)
+        // (envs that rewrote their window re-stage their own closes after the barrier; see the env branch)
+        if (col_ok) {
+            const float inv_f = s_inv[e];
+            const bool reload = IS_RESET || s_reload[e];
+            float *dst = tile + e * OBS + q * 5;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int k = q + 3 * i;
+                if (k < OLD) {
+                    float x0 = v[i][0], x1 = v[i][1], x2 = v[i][2], x3 = v[i][3];
+                    if (reload) {
+                        int slot = oldest + k;
+                        slot = slot >= HIST ? slot - HIST : slot;
+                        const float *o = obase + (long long)slot * 4 * n;
+                        x0 = ld_cg_f32(o);
+                        x1 = ld_cg_f32(o + n);
+                        x2 = ld_cg_f32(o + 2 * n);
+                        x3 = ld_cg_f32(o + 3 * n);
+                    }
+                    dst[i * 15 + 0] = x0 * inv_f;  // price_data / current_price, :513-515
+                    dst[i * 15 + 1] = x1 * inv_f;
+                    dst[i * 15 + 2] = x2 * inv_f;
+                    dst[i * 15 + 4] = x3 * inv_f;  // (index 3 is the close, written by the env thread)
+                }
+            }
+        }
+    } else {
+        // ======================================================================== env threads
+        const long long env = first + tid;
+        const bool active = env < n;
+        float *row = tile + tid * OBS;
+        double cash = 0.0, holdings = 0.0, cur = 1.0, rew = 0.0, value = 0.0, price_out = 0.0, ep_ret = 0.0;
+        float nw_o = 0.f, nw_h = 0.f, nw_l = 0.f, nw_v = 0.f;  // newest candle, float32 like the stored window
+        Market m{SIDEWAYS, 0.0, 0.5};
+        int step = 0, term = 0, trade = 0;
+        uint32_t flags = 0, ctr = 0;
+        bool reloaded = IS_RESET;
+        if (active) {
+            cash = a.st.scal[env];
+            holdings = a.st.scal[n + env];
+            m.trend = a.st.scal[2 * n + env];
+            m.psych = a.st.scal[3 * n + env];
+            const uint32_t meta = a.st.meta[env];
+            step = meta & 0xFFFF;
+            m.regime = (meta >> 16) & 0xFF;
+            flags = meta >> 24;
+            ctr = a.st.meta[n + env];
+            ep_ret = a.st.ep_return[env];
+
+            bool selected = true;
+            if constexpr (IS_RESET) {
+                if (a.mask) selected = a.mask[env] != 0;
+                if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
+                    m.regime = SIDEWAYS;
+                    m.trend = 0.0;
+                    m.psych = 0.5;
+                    ctr = 0;
+                }
+            }
+            EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
+
+            auto do_reset = [&]() {
+                cash = a.p.initial_balance;
+                holdings = 0.0;
+                step = 0;
+                flags = 0;
+                ep_ret = 0.0;
+                warmup_window(a, m, rng, env, head);
+                reloaded = true;
+            };
+
+            if constexpr (IS_RESET) {
+                if (selected) do_reset();
+            } else {
+                if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
+                    // The ring head moved by one slot with this call: rewrite the whole window at the new rotation.
+                    do_reset();
+                    price_out = a.st.close[(long long)head * n + env];
+                    value = cash + holdings * price_out;
+                } else {
+                    // _execute_action, :400-447
+                    const double price = a.st.close[(long long)a.p.window_head * n + env];
+                    const double initial_value = cash + holdings * price;
+                    if (a.p.action_type == 1) {
+                        const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
+                        const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
+                        const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
+                        if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
+                        else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
+                    } else {
+                        const long long act = reinterpret_cast<const long long *>(a.actions)[env];
+                        if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
+                        else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
+                        else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
+                        else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
+                        // anything else is a hold: the reference does not validate (:424-436)
+                    }
+                    const double final_value = cash + holdings * price;
+                    rew = final_value - initial_value;  // valued at the OLD price, :440-441
+                    if (!trade) rew -= 1.0;             // :444-445
+                    // next candle, :348-365
+                    const double volume = rng.uniform(0.5, 2.0);
+                    const double new_price = next_price(a.p, m, rng, price, volume);
+                    const double high = new_price * rng.uniform(1.0, 1.02);
+                    const double low = new_price * rng.uniform(0.98, 1.0);
+                    store_candle(a, env, head, price, high, low, new_price, volume);
+                    cur = new_price;
+                    nw_o = (float)price; nw_h = (float)high; nw_l = (float)low; nw_v = (float)volume;
+                    value = cash + holdings * new_price;
+                    price_out = new_price;
+                    step = min(step + 1, 65535);
+                    term = (step >= a.p.max_steps) || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
+                    ep_ret += rew;
+                    if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
+                        ended = true;
+                        st_ret = ep_ret;
+                        st_len = (double)step;
+                        st_val = value;
+                        if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
+                        if (a.io.ep_length) a.io.ep_length[env] = step;
+                        if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
+                        else flags |= CFLAG_NEEDS_RESET;
+                    }
+                }
+            }
+            if (reloaded) {  // newest candle from the (re)written window; same-thread read-after-write
+                cur = a.st.close[(long long)head * n + env];
+                const float *o = a.st.ohlv + ((long long)head * 4) * n + env;
+                nw_o = o[0]; nw_h = o[n]; nw_l = o[2 * n]; nw_v = o[3 * n];
+            }
+            ctr = rng.ctr;
+            s_inv[tid] = (float)(1.0 / cur);
+        }
+        s_reload[tid] = (uint8_t)(active && reloaded && !IS_RESET);
+        __threadfence_block();
+        __syncthreads();  // (A)
+        if (active) {
+            if (reloaded) {  // stage this env's 49 older closes again (its window changed in this launch)
+                for (int k = 0; k < OLD; ++k)
+                    s_close[k * T + tid] = ld_cg_f64(a.st.close + (long long)((oldest + k) % HIST) * n + env);
+            }
+            const float inv_f = s_inv[tid];
+            row[(HIST - 1) * 5 + 0] = nw_o * inv_f;
+            row[(HIST - 1) * 5 + 1] = nw_h * inv_f;
+            row[(HIST - 1) * 5 + 2] = nw_l * inv_f;
+            row[(HIST - 1) * 5 + 3] = (float)(cur * (1.0 / cur));
+            row[(HIST - 1) * 5 + 4] = nw_v * inv_f;
+            compose_indicators<T>(a.p, s_close, tid, cur, cash, holdings, m.psych, row);
+
+            a.st.scal[env] = cash;
+            a.st.scal[n + env] = holdings;
+            a.st.scal[2 * n + env] = m.trend;
+            a.st.scal[3 * n + env] = m.psych;
+            a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
+            a.st.meta[n + env] = ctr;
+            a.st.ep_return[env] = ep_ret;
+            if constexpr (!IS_RESET) {
+                a.io.reward[env] = (float)rew;
+                a.io.terminated[env] = (uint8_t)term;
+                if (a.io.truncated) a.io.truncated[env] = 0;
+                if (a.io.reward64) a.io.reward64[env] = rew;
+                if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
+                if (a.io.current_price) a.io.current_price[env] = price_out;
+                if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
+            }
         }
     }
 
     // drain the observation tile with one bulk asynchronous copy
     fence_proxy_async_smem();
-    __syncthreads();
+    __syncthreads();  // (B)
     if (tid == 0) {
         const long long n_here = min((long long)T, n - first);
         const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
@@ -390,23 +498,28 @@ __global__ void __launch_bounds__(T) crypto_kernel(const CArgs a) {
     }
 
     if constexpr (!IS_RESET) {
-        if (a.io.stats) {
+        if (a.io.stats && tid < T) {
             const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
             if (done_mask) {  // rare: ~1 step in 1000
-                const double r = warp_sum(st_ret), l = warp_sum(st_len), v = warp_sum(st_val);
+                const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
                 if ((tid & 31) == 0) {
                     atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
                     atomicAdd(&a.io.stats[1], r);
                     atomicAdd(&a.io.stats[2], l);
-                    atomicAdd(&a.io.stats[3], v);
+                    atomicAdd(&a.io.stats[3], v2);
                 }
             }
         }
     }
-    if (tid == 0) bulk_wait<0>();  // shared memory must outlive the copy
+    if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the copy engine's reads
 }
 
-constexpr int CRYPTO_T = 64;  // envs (= threads) per CTA: 64 x 1044 B = 66.8 KB tile, 3 CTAs per SM
+constexpr int CRYPTO_T = 32;  // envs per CTA (128 threads): 33.4 KB obs tile + 12.5 KB close staging, 4 CTAs per SM
+
+template <int T>
+constexpr size_t crypto_smem_bytes() {
+    return (size_t)T * OBS * sizeof(float) + (size_t)(HIST - 1) * T * sizeof(double) + T * sizeof(float) + T;
+}
 
 template <bool IS_RESET>
 int launch(const CArgs &a, cudaStream_t stream) {
@@ -418,14 +531,14 @@ int launch(const CArgs &a, cudaStream_t stream) {
     const int T = tile_env > 0 ? tile_env : CRYPTO_T;
 #define BENG_CCASE(TT)                                                                                          \
     if (T == TT) {                                                                                              \
-        const size_t smem = (size_t)TT * OBS * sizeof(float);                                                   \
+        const size_t smem = crypto_smem_bytes<TT>();                                                            \
         auto kern = crypto_kernel<TT, IS_RESET>;                                                                \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
         if (e != cudaSuccess) return (int)e;                                                                    \
-        kern<<<(unsigned)((a.n + TT - 1) / TT), TT, smem, stream>>>(a);                                         \
+        kern<<<(unsigned)((a.n + TT - 1) / TT), 4 * TT, smem, stream>>>(a);                                     \
         return finish_launch();                                                                                 \
     }
-    BENG_CCASE(32) BENG_CCASE(64) BENG_CCASE(96) BENG_CCASE(128) BENG_CCASE(192)
+    BENG_CCASE(32) BENG_CCASE(64) BENG_CCASE(128)
 #undef BENG_CCASE
     return BENG_ERR_UNSUPPORTED;
 }

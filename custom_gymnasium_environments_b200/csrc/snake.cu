@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
             if (pend_mask & (1u << lane)) a.io.done_env[base + __popc(pend_mask & ((1u << lane) - 1u))] = pend_env;
         }
     }
-    if (tid == 0) bulk_wait<0>();  // all tiles written before the CTA (and its shared memory) retires
+    if (tid == 0) bulk_wait_read<0>();  // the copy engine has read every tile before the CTA's shared memory retires
     if constexpr (!IS_RESET) {
         if (a.io.stats) {
             __syncthreads();
