@@ -45,6 +45,21 @@ class CryptoIO(C.Structure):
         "ep_return_out", "ep_length", "stats")]
 
 
+class TrafficParams(C.Structure):
+    _fields_ = [("grid_rows", C.c_int32), ("grid_cols", C.c_int32), ("num_intersections", C.c_int32),
+                ("max_vehicles", C.c_int32), ("spawn_rate", C.c_double), ("max_timesteps", C.c_int32),
+                ("autoreset_mode", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+
+
+class TrafficState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("light", "passed", "waiting", "qmeta", "qwait", "misc", "total_reward")]
+
+
+class TrafficIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "terminated", "truncated", "reward64", "ep_return",
+                                          "ep_length", "stats")]
+
+
 # name -> (restype, argtypes); also the list of symbols include/beng.h declares (tests check it).
 SIGNATURES = {
     "beng_version": (C.c_int, []),
@@ -68,6 +83,12 @@ SIGNATURES = {
                                    C.c_int64, C.c_void_p]),
     "beng_crypto_step_host": (C.c_int, [C.POINTER(CryptoParams), C.POINTER(CryptoState), C.c_void_p,
                                         C.POINTER(CryptoIO), C.c_int64] + [C.c_void_p] * 6),
+    "beng_traffic_reset": (C.c_int, [C.POINTER(TrafficParams), C.POINTER(TrafficState), C.POINTER(TrafficIO),
+                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "beng_traffic_step": (C.c_int, [C.POINTER(TrafficParams), C.POINTER(TrafficState), C.c_void_p,
+                                    C.POINTER(TrafficIO), C.c_int64, C.c_void_p]),
+    "beng_traffic_step_host": (C.c_int, [C.POINTER(TrafficParams), C.POINTER(TrafficState), C.c_void_p,
+                                         C.POINTER(TrafficIO), C.c_int64] + [C.c_void_p] * 6),
     "beng_snake_export_state": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_int64] +
                                 [C.c_void_p] * 10),
 }

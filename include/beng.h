@@ -220,6 +220,67 @@ int beng_crypto_step_host(const beng_crypto_params *p, const beng_crypto_state *
                           const beng_crypto_io *io, int64_t n_envs, const void *actions_host, float *obs_host,
                           float *reward_host, uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * traffic_management_env  (reference: traffic_management_env/{environment,utils,config}.py)
+ * ------------------------------------------------------------------------------------------ */
+
+#define BENG_TRAFFIC_MAX_INTERSECTIONS 25
+
+/* Constructor arguments of TrafficManagementEnv (environment.py:61-66, defaults config.py:6-12) + config.py
+ * MAX_TIMESTEPS + batching parameters.  The remaining config.py constants (phase durations 5/30/3, reward weights
+ * 1.0/-0.1/-0.05/0.5, observation caps 20/100/1000/50) are compiled in. */
+typedef struct beng_traffic_params {
+    int32_t grid_rows, grid_cols; /* grid_size, default (5, 5) */
+    int32_t num_intersections;    /* default 9; effective value = min(this, rows*cols) (environment.py:82); <= 25 */
+    int32_t max_vehicles;         /* default 50; <= 255 */
+    double spawn_rate;            /* default 0.3 */
+    int32_t max_timesteps;        /* config.py:23 MAX_TIMESTEPS = 1000 */
+    int32_t autoreset_mode;       /* BENG_AUTORESET_* */
+    uint64_t seed;
+    uint64_t env_id_base;
+} beng_traffic_params;
+
+/* Per-env state, [field][env] arrays (env index fastest).  Vehicles never move in the reference (SURVEY.md
+ * section 0 fact 9), so a queue is fully described by (length, sum of waiting times, number of vehicles whose
+ * route ends where it started) and the env by the length of `self.vehicles`. */
+typedef struct beng_traffic_state {
+    uint16_t *light;      /* [ni][n]    phase (low byte: 0 NS_GREEN 1 NS_YELLOW 2 EW_GREEN 3 EW_YELLOW) | timer << 8 */
+    int32_t *passed;      /* [ni][n]    Intersection.vehicles_passed */
+    int32_t *waiting;     /* [ni][n]    Intersection.total_waiting_time */
+    uint16_t *qmeta;      /* [ni*4][n]  queue length | loop-back vehicles << 8, directions N, E, S, W */
+    int32_t *qwait;       /* [ni*4][n]  sum of Vehicle.waiting_time over the queue */
+    uint32_t *misc;       /* [3][n]     current_timestep | flags << 16 ; len(self.vehicles) ; rng_counter */
+    double *total_reward; /* [n]        running episode return (info["total_reward"]) */
+} beng_traffic_state;
+
+typedef struct beng_traffic_io {
+    float *obs;            /* [n][ni*14+4]  _get_observation (environment.py:313-363) */
+    float *reward;         /* [n]           _calculate_reward (:287-311) cast to float32 */
+    uint8_t *terminated;   /* [n]           current_timestep >= MAX_TIMESTEPS (:196) */
+    uint8_t *truncated;    /* [n]           always 0 (:197) */
+    double *reward64;      /* [n] nullable  the float64 reward */
+    double *ep_return;     /* [n] nullable  written when an episode ends (auto-reset modes) */
+    int32_t *ep_length;    /* [n] nullable */
+    double *stats;         /* [3] nullable  running {n_episodes, sum_return, sum_length} */
+} beng_traffic_io;
+
+/* TrafficManagementEnv.reset (environment.py:141-166) for envs with mask[i] != 0 (NULL = all); first_call != 0 also
+ * rewinds the rng counter.  The observation of EVERY env is written to io->obs. */
+int beng_traffic_reset(const beng_traffic_params *p, const beng_traffic_state *st, const beng_traffic_io *io,
+                       const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream);
+
+/* TrafficManagementEnv.step (environment.py:168-203): _apply_actions, every TrafficLight.update, _spawn_vehicles
+ * (+ generate_vehicle_route), _process_intersections, _remove_completed_vehicles, _calculate_reward,
+ * _get_observation and auto-reset, for all envs, in ONE kernel launch.  actions_dev: int64 [n][ni], values
+ * 0 keep / 1 NS_GREEN / 2 EW_GREEN (anything else keeps, like the reference). */
+int beng_traffic_step(const beng_traffic_params *p, const beng_traffic_state *st, const int64_t *actions_dev,
+                      const beng_traffic_io *io, int64_t n_envs, void *stream);
+
+/* Same step with HOST action / result buffers; NULL host outputs are skipped; does not synchronise. */
+int beng_traffic_step_host(const beng_traffic_params *p, const beng_traffic_state *st, int64_t *actions_dev,
+                           const beng_traffic_io *io, int64_t n_envs, const int64_t *actions_host, float *obs_host,
+                           float *reward_host, uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,15 @@ def lib():
         _lib.crypto_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
         _lib.crypto_oracle_set_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
         _lib.crypto_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.traffic_oracle_create.restype = C.c_void_p
+        _lib.traffic_oracle_create.argtypes = [C.c_int] * 5 + [C.c_double, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
+        _lib.traffic_oracle_destroy.argtypes = [C.c_void_p]
+        _lib.traffic_oracle_obs_dim.restype = C.c_int
+        _lib.traffic_oracle_obs_dim.argtypes = [C.c_void_p]
+        _lib.traffic_oracle_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.traffic_oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        _lib.traffic_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 10
+        _lib.traffic_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib.beng_oracle_draws_u32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.beng_oracle_action_tape.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_int,
                                                  C.c_void_p]
@@ -200,3 +209,58 @@ class CryptoOracle:
         out = np.zeros(4, np.float64)
         lib().crypto_oracle_get_stats(self._h, _p(out))
         return dict(zip(["n_episodes", "sum_return", "sum_length", "sum_final_value"], out.tolist()))
+
+
+class TrafficOracle:
+    """Batched CPU oracle with the same outputs as the device engine's traffic step."""
+
+    def __init__(self, n_envs, grid_size=(5, 5), num_intersections=9, max_vehicles=50, spawn_rate=0.3, seed=0,
+                 env_id_base=0, autoreset="same_step", max_timesteps=1000):
+        self.n = int(n_envs)
+        self._h = C.c_void_p(lib().traffic_oracle_create(self.n, grid_size[0], grid_size[1], num_intersections,
+                                                          max_vehicles, spawn_rate, max_timesteps, seed, env_id_base,
+                                                          AUTORESET[autoreset]))
+        self.ni = min(num_intersections, grid_size[0] * grid_size[1])
+        self.obs_dim = lib().traffic_oracle_obs_dim(self._h)
+        n = self.n
+        self.obs = np.zeros((n, self.obs_dim), np.float32)
+        self.reward = np.zeros(n, np.float32)
+        self.reward64 = np.zeros(n, np.float64)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+        self.ep_return = np.zeros(n, np.float64)
+        self.ep_length = np.zeros(n, np.int32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().traffic_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().traffic_oracle_reset(self._h, _p(m), _p(self.obs))
+        return self.obs
+
+    def step(self, actions, want_obs=True):
+        a = np.ascontiguousarray(actions, np.int64)
+        assert a.shape == (self.n, self.ni)
+        lib().traffic_oracle_step(self._h, _p(a), _p(self.obs) if want_obs else None, _p(self.reward),
+                                  _p(self.terminated), _p(self.truncated), _p(self.reward64), _p(self.ep_return),
+                                  _p(self.ep_length))
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    def state(self):
+        n, ni = self.n, self.ni
+        d = {"timestep": np.zeros(n, np.int32), "num_vehicles": np.zeros(n, np.int32),
+             "rng_counter": np.zeros(n, np.uint32), "total_reward": np.zeros(n, np.float64),
+             "phase": np.zeros((n, ni), np.int32), "timer": np.zeros((n, ni), np.int32),
+             "passed": np.zeros((n, ni), np.int32), "waiting": np.zeros((n, ni), np.int32),
+             "qlen": np.zeros((n, ni, 4), np.int32), "qwait": np.zeros((n, ni, 4), np.int32)}
+        lib().traffic_oracle_get_state(self._h, *[_p(d[k]) for k in ("timestep", "num_vehicles", "rng_counter",
+                                       "total_reward", "phase", "timer", "passed", "waiting", "qlen", "qwait")])
+        return d
+
+    def stats(self):
+        out = np.zeros(3, np.float64)
+        lib().traffic_oracle_get_stats(self._h, _p(out))
+        return dict(zip(["n_episodes", "sum_return", "sum_length"], out.tolist()))
