@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the batched env-step hot path (BASELINE.json: env-steps/sec; headline = batched SnakeEnv, 1M envs/GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--env snake|crypto]   # this repo's CUDA engine
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--env snake|crypto|traffic]   # this repo's CUDA engine
     python bench.py --impl reference [--gpus N] --steps K --warmup W [--env …]  # CPU arm: the reference's step loop
 
 A "step" is ONE launch of the fused step kernel over the whole batch, inputs resident in HBM; `value` =
@@ -54,6 +54,10 @@ WORKLOADS = {
     "crypto": Workload("crypto", 1 << 18, 2190, 5, 1, "f64",
                        "batched CryptoTradingEnv, discrete actions, default TradingConfig, fp64 dynamics / fp32 obs, "
                        "SAME_STEP auto-reset (BASELINE.json configs[2])", 1044, 4 + 1 + 1, 300),
+    # obs 520 W + actions 72 R + reward/flags 6 + lights 36 + vehicle pool 400 + counters 144 + scalars 32
+    "traffic": Workload("traffic", 1 << 16, 1210, 3, 9, "i32",
+                        "batched TrafficManagementEnv, default config (9 intersections, 50 vehicles, spawn 0.3), "
+                        "SAME_STEP auto-reset (BASELINE.json configs[3])", 520, 4 + 1 + 1, 600),
 }
 
 
@@ -71,20 +75,32 @@ def _cpu_worker_loop(args):
         from oracle.snake_port import SnakePort
 
         env, n_act = SnakePort(20, rng=rng), 4
-    else:
+    elif env_name == "crypto":
         import numpy as np
 
         from oracle.crypto_port import CryptoPort
 
         np.random.seed(1234 + worker)
         env, n_act = CryptoPort(action_type="discrete"), 5
+    else:
+        import numpy as np
+
+        from oracle.traffic_port import TrafficPort
+
+        env, n_act = TrafficPort(rng=rng), 3
     env.reset()
     randrange = rng.randrange
     t0 = time.perf_counter()
-    for _ in range(n_steps):
-        _, _, term, trunc, _ = env.step(randrange(n_act))
-        if term or trunc:
-            env.reset()
+    if env_name == "traffic":
+        for _ in range(n_steps):  # MultiDiscrete([3]*9) sample, like env.action_space.sample() in traffic test_env.py:266-278
+            _, _, term, trunc, _ = env.step(np.array([randrange(3) for _ in range(9)]))
+            if term or trunc:
+                env.reset()
+    else:
+        for _ in range(n_steps):
+            _, _, term, trunc, _ = env.step(randrange(n_act))
+            if term or trunc:
+                env.reset()
     return n_steps, time.perf_counter() - t0
 
 
@@ -114,10 +130,14 @@ def c_oracle_rate(env_name: str, seconds: float = 1.5) -> float:
         n = 1 << 15
         orc = c_oracle.SnakeOracle(n, seed=0)
         acts = rng.integers(0, 4, (16, n))
-    else:
+    elif env_name == "crypto":
         n = 1 << 11
         orc = c_oracle.CryptoOracle(n, seed=0)
         acts = rng.integers(0, 5, (16, n))
+    else:
+        n = 1 << 10
+        orc = c_oracle.TrafficOracle(n, seed=0)
+        acts = rng.integers(0, 3, (16, n, 9))
     orc.reset()
     orc.step(acts[0])
     t0 = time.perf_counter()
@@ -130,7 +150,10 @@ def c_oracle_rate(env_name: str, seconds: float = 1.5) -> float:
 
 def port_description(env_name, cores, per_proc):
     what = {"snake": "SnakeEnvClassic (oracle/snake_port.py), G=20",
-            "crypto": "CryptoTradingEnv (oracle/crypto_port.py), discrete actions"}[env_name]
+            "crypto": "CryptoTradingEnv (oracle/crypto_port.py), discrete actions",
+            "traffic": "TrafficManagementEnv (oracle/traffic_port.py; measured 1.5x FASTER than the real reference "
+                       "in the build container, 2.9k vs 1.9k steps/s, so a conservative baseline), default config"
+            }[env_name]
     return (f"pure-Python port of {what}: 1 env per process x {cores} processes x {per_proc} random-action "
             "steps with reset-on-done")
 
@@ -233,12 +256,17 @@ class ClockSampler:
 def workload_config(args, per_gpu):
     w = WORKLOADS[args.env]
     mb = per_gpu * w.bytes / 1e6
+    if per_gpu * w.bytes < 2 * 126e6 and not getattr(args, "no_l2_flush", False):
+        l2 = (f"L2 flushed between timed steps: one step moves only {mb:.0f} MB (< 126 MB L2), so every step is timed "
+              "on its own CUDA events with an untimed 256 MB fill before it")
+    else:
+        l2 = (f"inputs larger than L2: each step streams {mb:.0f} MB through a 126 MB L2; the action tape cycles "
+              "over >= 64 distinct tensors")
     return {"workload": w.label, "env": w.name,
             "envs_per_gpu": per_gpu, "global_envs": per_gpu * args.gpus, "max_steps": 1000,
             "actions": f"i.i.d. uniform{{0..{w.n_choices - 1}}} int64, device-generated tape (Philox stream 1), "
                        "resident in HBM",
-            "l2_policy": f"inputs larger than L2: each step streams {mb:.0f} MB through a 126 MB L2; the action tape "
-                         "cycles over >= 64 distinct tensors",
+            "l2_policy": l2,
             "parallelism": f"env-sharded x{args.gpus}, no data-path collective"}
 
 
@@ -264,7 +292,9 @@ def load_traffic(env_name, n_envs):
 def make_env(pkg, env_name, n, dev, seed, base):
     if env_name == "snake":
         return pkg.BatchedSnakeEnv(n, 20, device=dev, seed=seed, env_id_base=base)
-    return pkg.BatchedCryptoTradingEnv(n, None, "discrete", device=dev, seed=seed, env_id_base=base)
+    if env_name == "crypto":
+        return pkg.BatchedCryptoTradingEnv(n, None, "discrete", device=dev, seed=seed, env_id_base=base)
+    return pkg.BatchedTrafficManagementEnv(n, device=dev, seed=seed, env_id_base=base)
 
 
 def kernel_description(lib, env_name, n):
@@ -275,7 +305,10 @@ def kernel_description(lib, env_name, n):
         lib.beng_snake_launch_config(20, n, C.byref(t_), C.byref(s_), C.byref(c_))
         return (f"beng::snake_kernel<T={t_.value},STAGES={s_.value},IS_RESET=false,OWNROW=true>, "
                 f"{c_.value} persistent CTAs/SM")
-    return "beng::crypto_kernel<T=32,IS_RESET=false>: 128-thread warp-specialised CTA per 32-env tile (1 env warp + 3 window warps)"
+    if env_name == "crypto":
+        return ("beng::crypto_kernel<T=32,IS_RESET=false>: 128-thread warp-specialised CTA per 32-env tile "
+                "(1 env warp + 3 window warps)")
+    return "beng::traffic_kernel<NI=9,T=64,IS_RESET=false>: one thread per env, 64-env tile per CTA"
 
 
 def run_b200_arm(args):
@@ -307,9 +340,10 @@ def run_b200_arm(args):
 
     # action tapes, resident in HBM before the timed region (pool of distinct steps, cycled)
     pool = max(64, min(args.steps + args.warmup, args.action_pool))
-    tapes = torch.empty((pool, n), dtype=torch.int64, device=dev)
+    tape_shape = (pool, n) if w.n_cols == 1 else (pool, n, w.n_cols)
+    tapes = torch.empty(tape_shape, dtype=torch.int64, device=dev)
     for t in range(pool):
-        pkg._lib.check(lib.beng_fill_random_actions(tapes[t].data_ptr(), n, 1, w.n_choices, t, base, seed,
+        pkg._lib.check(lib.beng_fill_random_actions(tapes[t].data_ptr(), n, w.n_cols, w.n_choices, t, base, seed,
                                                     stream.cuda_stream), "beng_fill_random_actions")
     torch.cuda.synchronize(dev)
 
@@ -318,6 +352,11 @@ def run_b200_arm(args):
             dist.barrier()
 
     # ---- device-resident timing -----------------------------------------------------------------
+    # Timing rule: inputs larger than L2, or L2 flushed between timed iterations.  Snake (472 MB/step) and crypto
+    # (574 MB/step) stream far more than the 126 MB L2 every step.  Traffic at its BASELINE size moves ~79 MB per
+    # step, which would stay L2-resident: there every step is timed on its own events with a 256 MB fill in between
+    # (the warm, back-to-back figure is reported separately as `value_l2_warm`).
+    flush = n * w.bytes < 2 * 126e6 and not args.no_l2_flush
     for t in range(args.warmup):
         env.step(tapes[t % pool])
     torch.cuda.synchronize(dev)
@@ -332,20 +371,35 @@ def run_b200_arm(args):
         env.step(tapes[(args.warmup + t) % pool])
     ev1.record(stream)
     torch.cuda.synchronize(dev)
-    sampler.stop()
     launches = lib.beng_launch_count() - launches0
+    ms_warm = ev0.elapsed_time(ev1)
+    ms = ms_warm
+    if flush:
+        scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        launches0 = lib.beng_launch_count()
+        for t in range(args.steps):
+            scratch.fill_(t & 0xFF)  # evicts the previous step's lines from L2 (not timed)
+            pairs[t][0].record(stream)
+            env.step(tapes[(args.warmup + t) % pool])
+            pairs[t][1].record(stream)
+        torch.cuda.synchronize(dev)
+        launches = lib.beng_launch_count() - launches0
+        ms = sum(a.elapsed_time(b) for a, b in pairs)
+        del scratch
+    sampler.stop()
     barrier()
-    ms = ev0.elapsed_time(ev1)
     ms_t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_max = float(ms_t.item())
     value = n * world * args.steps / (ms_max * 1e-3)
+    value_warm = n * world * args.steps / (ms_warm * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI call -------------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     host_tapes = [tapes[t % pool].cpu().pin_memory() for t in range(min(e2e_steps + 2, 8))]
-    h2d = n * 8
+    h2d = n * 8 * w.n_cols
     d2h_full = n * (w.obs_bytes + w.result_bytes)
     d2h_lite = n * w.result_bytes
 
@@ -378,7 +432,9 @@ def run_b200_arm(args):
             dist.all_reduce(st, op=dist.ReduceOp.SUM)
         v = st.tolist()
         summary = {"episodes": int(v[0]), "episode_return_mean": v[1] / max(v[0], 1),
-                   "episode_len_mean": v[2] / max(v[0], 1), "final_value_mean": v[3] / max(v[0], 1)}
+                   "episode_len_mean": v[2] / max(v[0], 1)}
+        if args.env == "crypto":
+            summary["final_value_mean"] = v[3] / max(v[0], 1)
 
     if rank != 0:
         if world > 1:
@@ -390,7 +446,8 @@ def run_b200_arm(args):
     per_launch_ms = ms / max(1, args.steps)  # rank-0 kernel time; the timed region is back-to-back step launches
     achieved = n * w.bytes / (per_launch_ms * 1e-3) / 1e9
     api = {"snake": "BatchedSnakeEnv.step_host -> beng_snake_step_host",
-           "crypto": "BatchedCryptoTradingEnv.step_host -> beng_crypto_step_host"}[args.env]
+           "crypto": "BatchedCryptoTradingEnv.step_host -> beng_crypto_step_host",
+           "traffic": "BatchedTrafficManagementEnv.step_host -> beng_traffic_step_host"}[args.env]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
@@ -408,6 +465,8 @@ def run_b200_arm(args):
                               "note": "same call with obs_host=NULL: reward/terminated/info to host, observation "
                                       "stays in HBM for an on-device policy"},
         "gpu_launches": int(launches),
+        "l2_flushed_between_steps": bool(flush),
+        "value_l2_warm": value_warm if flush else None,
         "clocks": sampler.summary(),
         "episodes": summary,
     }
@@ -435,11 +494,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--env", choices=sorted(WORKLOADS), default="snake",
-                    help="snake = the BASELINE.json headline (configs[1]); crypto = configs[2]")
+                    help="snake = the BASELINE.json headline (configs[1]); crypto = configs[2]; traffic = configs[3]")
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--action-pool", type=int, default=256, help="distinct pre-generated action steps kept in HBM")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true", help="traffic only: time back-to-back steps (L2-warm)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.envs_per_gpu is None:

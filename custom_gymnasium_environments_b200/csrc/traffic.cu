@@ -125,14 +125,36 @@ __global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
         }
         EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
 
+        // Bring the whole env state into registers with independent, fully coalesced loads issued back to back (one
+        // round of memory latency instead of one per intersection); everything below works on these copies.
+        uint32_t L[CAP], QM[CAP * 4];
+        int P[CAP], Wt[CAP], QW[CAP * 4];
+        long long ACT[CAP];
+#pragma unroll
+        for (int i = 0; i < CAP; ++i) {
+            if (i < NI) {
+                L[i] = a.st.light[(long long)i * n + env];
+                P[i] = a.st.passed[(long long)i * n + env];
+                Wt[i] = a.st.waiting[(long long)i * n + env];
+                if constexpr (!IS_RESET) ACT[i] = a.actions[env * NI + i];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    QM[i * 4 + d] = a.st.qmeta[(long long)(i * 4 + d) * n + env];
+                    QW[i * 4 + d] = a.st.qwait[(long long)(i * 4 + d) * n + env];
+                }
+            }
+        }
+
         int sp_i = -1, sp_d = 0, sp_lb = 0;  // vehicle spawned this step: start intersection, direction, loop-back
         if (!IS_RESET && !do_reset) {
             timestep = min(timestep + 1, 65535);  // :170
             // _apply_actions (:205-220) then TrafficLight.update (utils.py:79-97), lights in id order
-            for (int i = 0; i < NI; ++i) {
-                const uint32_t l = a.st.light[(long long)i * n + env];
+#pragma unroll
+            for (int i = 0; i < CAP; ++i) {
+                if (i >= NI) break;
+                const uint32_t l = L[i];
                 int phase = l & 0xFF, timer = (int)(l >> 8);
-                const long long act = a.actions[env * NI + i];
+                const long long act = ACT[i];
                 if (act == 1 && phase != NS_GREEN) { phase = NS_GREEN; timer = 5; }       // set_phase: MIN_PHASE_DURATION
                 else if (act == 2 && phase != EW_GREEN) { phase = EW_GREEN; timer = 5; }
                 timer -= 1;
@@ -142,6 +164,7 @@ __global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
                 }
                 const uint32_t nl = (uint32_t)phase | ((uint32_t)timer << 8);
                 if (nl != l) a.st.light[(long long)i * n + env] = (uint16_t)nl;
+                L[i] = nl;
             }
             // _spawn_vehicles (:222-249)
             if (listed < a.p.max_vehicles) {
@@ -165,9 +188,9 @@ __global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
                     a.st.passed[(long long)i * n + env] = 0;
                     a.st.waiting[(long long)i * n + env] = 0;
                 } else {
-                    phase = a.st.light[(long long)i * n + env] & 0xFF;
-                    passed = a.st.passed[(long long)i * n + env];
-                    wait = a.st.waiting[(long long)i * n + env];
+                    phase = L[i] & 0xFF;
+                    passed = P[i];
+                    wait = Wt[i];
                 }
                 const int passed0 = passed, wait0 = wait;
                 int qsum = 0;
@@ -181,8 +204,8 @@ __global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
                         a.st.qmeta[qi] = 0;
                         a.st.qwait[qi] = 0;
                     } else {
-                        qm0 = a.st.qmeta[qi];
-                        qw0 = a.st.qwait[qi];
+                        qm0 = QM[i * 4 + d];
+                        qw0 = QW[i * 4 + d];
                         cnt = qm0 & 0xFF;
                         lb = qm0 >> 8;
                         qw = qw0;
