@@ -9,7 +9,7 @@
 //   CryptoTradingEnv.reset :301-340, step :342-398, _execute_action :400-447, _execute_buy :449-476,
 //                   _execute_sell :478-503, _get_observation :505-561
 //
-// Design (DESIGN.md section 9):
+// Design (DESIGN.md section 7):
 //   * one THREAD per env; every state array is laid out [slot/field][env] so that a warp's accesses are
 //     contiguous (the 50-candle window is read as 250 fully coalesced loads per thread, high ILP);
 //   * the window is a ring over 50 slots with ONE head shared by all envs (params.window_head): a step
