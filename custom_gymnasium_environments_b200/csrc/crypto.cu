@@ -97,29 +97,40 @@ __device__ __forceinline__ double next_price(const beng_crypto_params &p, Market
     return np_;
 }
 
-__device__ __forceinline__ void store_candle(const CArgs &a, long long env, int slot, double open, double high,
-                                             double low, double close, double volume) {
-    a.st.close[(long long)slot * a.n + env] = close;
-    float *o = a.st.ohlv + ((long long)slot * 4) * a.n + env;
+__device__ __forceinline__ void store_candle(double *close_arr, float *ohlv_arr, long long n, long long env, int slot,
+                                             double open, double high, double low, double close, double volume) {
+    close_arr[(long long)slot * n + env] = close;
+    float *o = ohlv_arr + ((long long)slot * 4) * n + env;
     o[0] = (float)open;
-    o[a.n] = (float)high;
-    o[2 * a.n] = (float)low;
-    o[3 * a.n] = (float)volume;
+    o[n] = (float)high;
+    o[2 * n] = (float)low;
+    o[3 * n] = (float)volume;
 }
 
 // reset, :301-340: 50 warm-up candles from 50000.0; the newest lands in slot `head`.  Market state carries over.
-__device__ __noinline__ void warmup_window(const CArgs &a, Market &m, EnvStream &rng, long long env, int head) {
+// Deliberately NOT inlined (it runs once per 1000 steps) and deliberately BY VALUE: taking the address of the
+// caller's market / RNG state or of the kernel parameter block would force them into local memory for every
+// thread on the hot path (measured: 135 us of a 300 us step).
+struct WarmupResult {
+    Market m;
+    uint32_t ctr;
+};
+__device__ __noinline__ WarmupResult warmup_window(double *close_arr, float *ohlv_arr, long long n, long long env,
+                                                   int head, beng_crypto_params p, Market m, uint64_t gid,
+                                                   uint32_t ctr) {
+    EnvStream rng(p.seed, gid, BENG_STREAM_ENV, ctr);
     double price = 50000.0;
     int slot = head + 1 == HIST ? 0 : head + 1;  // oldest
     for (int k = 0; k < HIST; ++k) {
         const double volume = rng.uniform(0.5, 2.0);
-        price = next_price(a.p, m, rng, price, volume);
+        price = next_price(p, m, rng, price, volume);
         const double high = price * rng.uniform(1.0, 1.02);
         const double low = price * rng.uniform(0.98, 1.0);
         const double open = price * rng.uniform(0.99, 1.01);
-        store_candle(a, env, slot, open, high, low, price, volume);
+        store_candle(close_arr, ohlv_arr, n, env, slot, open, high, low, price, volume);
         slot = slot + 1 == HIST ? 0 : slot + 1;
     }
+    return WarmupResult{m, rng.ctr};
 }
 
 // NumPy's pairwise summation order for 8 <= n <= 128 (np.mean / np.std in the reference), n static.
@@ -142,18 +153,20 @@ __device__ __forceinline__ double np_sum(const double (&v)[N]) {
 // Indicator part of _get_observation (:519-559) for one env, plus the normalised close column.
 // `closes` is the CTA's staging area [HIST-1][T] (float64, oldest first) holding the 49 older closes of every env
 // in the tile; `cur` is the newest close.  Writes row[k*5+3] for k < 49 and row[250..260].
-template <int T>
-__device__ __forceinline__ void compose_indicators(const beng_crypto_params &p, const double *closes, int lane_env,
-                                                   double cur, double cash, double holdings, double psych,
-                                                   float *row) {
+// `close_at(k)` returns the k-th oldest close (k < 49); WRITE_CLOSE_COL selects whether the normalised close column
+// row[k*5+3] is written here.  `row` receives 250.. as row[250+i] when TAIL_ONLY is false, else tail[i] = feature 250+i.
+template <bool WRITE_CLOSE_COL, typename CloseAt>
+__device__ __forceinline__ void compose_indicators(const beng_crypto_params &p, CloseAt close_at, double cur,
+                                                   double cash, double holdings, double psych, float *row,
+                                                   float *tail) {
     const double inv = 1.0 / cur;
     const double mf = 2.0 / 13.0, ms = 2.0 / 27.0, mg = 2.0 / 10.0;  // _ema multipliers, :113
     double ef = 0.0, es = 0.0, sig = 0.0, mx = 0.0, mn = 0.0;
     double w[20];  // the last 20 closes (Bollinger window; its last 15 give the 14 RSI deltas)
 #pragma unroll
     for (int k = 0; k < HIST; ++k) {
-        const double c = (k == HIST - 1) ? cur : closes[k * T + lane_env];
-        if (k < HIST - 1) row[k * 5 + 3] = (float)(c * inv);  // close / current_price, :513-515
+        const double c = (k == HIST - 1) ? cur : close_at(k);
+        if (WRITE_CLOSE_COL && k < HIST - 1) row[k * 5 + 3] = (float)(c * inv);  // close / current_price, :513-515
         if (k == 0) {
             ef = es = mx = mn = c;  // _ema seeds at prices[0], :114
         } else {
@@ -168,9 +181,9 @@ __device__ __forceinline__ void compose_indicators(const beng_crypto_params &p, 
     }
 
     const double value = cash + holdings * cur;  // :519-527
-    row[250] = (float)(cash / p.initial_balance);
-    row[251] = (float)(holdings * cur / p.initial_balance);
-    row[252] = (float)(value / p.initial_balance);
+    tail[0] = (float)(cash / p.initial_balance);
+    tail[1] = (float)(holdings * cur / p.initial_balance);
+    tail[2] = (float)(value / p.initial_balance);
 
     // RSI(14) over the last 14 deltas, :45-61
     double g[14], l[14];
@@ -186,16 +199,16 @@ __device__ __forceinline__ void compose_indicators(const beng_crypto_params &p, 
         const double rs = avg_gain / avg_loss;
         rsi = 100.0 - (100.0 / (1.0 + rs));
     }
-    row[253] = (float)(rsi / 100.0);
+    tail[3] = (float)(rsi / 100.0);
 
     // MACD(12, 26, 9) normalised by the close range, :538-547
     const double macd_line = ef - es, hist = macd_line - sig, range = mx - mn;
     if (range > 0) {
-        row[254] = (float)(macd_line / range);
-        row[255] = (float)(sig / range);
-        row[256] = (float)(hist / range);
+        tail[4] = (float)(macd_line / range);
+        tail[5] = (float)(sig / range);
+        tail[6] = (float)(hist / range);
     } else {
-        row[254] = row[255] = row[256] = 0.0f;
+        tail[4] = tail[5] = tail[6] = 0.0f;
     }
 
     // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
@@ -208,10 +221,10 @@ __device__ __forceinline__ void compose_indicators(const beng_crypto_params &p, 
     }
     const double sd = sqrt(np_sum(sq) / 20.0);
     const double upper = sma + (2 * sd), lower = sma - (2 * sd);
-    row[257] = (float)((upper > lower) ? (cur - lower) / (upper - lower) : 0.5);
-    row[258] = (float)((sma > 0) ? (upper - lower) / sma : 0.0);
-    row[259] = (float)((sma > 0) ? (cur - sma) / sma : 0.0);
-    row[260] = (float)psych;  // :559
+    tail[7] = (float)((upper > lower) ? (cur - lower) / (upper - lower) : 0.5);
+    tail[8] = (float)((sma > 0) ? (upper - lower) / sma : 0.0);
+    tail[9] = (float)((sma > 0) ? (cur - sma) / sma : 0.0);
+    tail[10] = (float)psych;  // :559
 }
 
 // L2-coherent loads (bypass L1) for data another thread of this CTA may have just rewritten.
@@ -384,7 +397,10 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
                 step = 0;
                 flags = 0;
                 ep_ret = 0.0;
-                warmup_window(a, m, rng, env, head);
+                const WarmupResult wr = warmup_window(a.st.close, a.st.ohlv, n, env, head, a.p, m,
+                                                      a.p.env_id_base + (uint64_t)env, rng.ctr);
+                m = wr.m;
+                rng = EnvStream(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, wr.ctr);
                 reloaded = true;
             };
 
@@ -422,7 +438,7 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
                     const double new_price = next_price(a.p, m, rng, price, volume);
                     const double high = new_price * rng.uniform(1.0, 1.02);
                     const double low = new_price * rng.uniform(0.98, 1.0);
-                    store_candle(a, env, head, price, high, low, new_price, volume);
+                    store_candle(a.st.close, a.st.ohlv, n, env, head, price, high, low, new_price, volume);
                     cur = new_price;
                     nw_o = (float)price; nw_h = (float)high; nw_l = (float)low; nw_v = (float)volume;
                     value = cash + holdings * new_price;
@@ -464,7 +480,8 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
             row[(HIST - 1) * 5 + 2] = nw_l * inv_f;
             row[(HIST - 1) * 5 + 3] = (float)(cur * (1.0 / cur));
             row[(HIST - 1) * 5 + 4] = nw_v * inv_f;
-            compose_indicators<T>(a.p, s_close, tid, cur, cash, holdings, m.psych, row);
+            compose_indicators<true>(a.p, [&](int k) { return s_close[k * T + tid]; }, cur, cash, holdings, m.psych, row,
+                                     row + 250);
 
             a.st.scal[env] = cash;
             a.st.scal[n + env] = holdings;
@@ -514,6 +531,269 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
     if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the copy engine's reads
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two-phase CTA (the default): 256 threads own 256 consecutive envs.
+//   phase 1  one thread per env: trade, price walk, candle, termination, auto-reset and the indicator scans, closes
+//            read straight from global memory (coalesced over envs).  No observation staging is needed here, so 512
+//            env threads are resident per SM (4x the warp-specialised kernel above) to hide the long serial float64
+//            chain.  Each thread leaves 1/close and its 11 indicator features in shared memory.
+//   phase 2  all 256 threads stream the window of eight 32-env sub-tiles: thread (e = tid % 32, g = tid / 32) handles
+//            slots k = g, g+8, ... of env e, normalises open/high/low/close/volume into a double-buffered 33 KB
+//            observation tile, which one thread drains with a bulk asynchronous copy while the next sub-tile is built.
+// Window reads in phase 2 are L2-coherent (ld.global.cg): an env that auto-reset rewrote its window in phase 1.
+constexpr int C2_ENVS = 256, C2_SUB = 32, C2_GROUPS = C2_ENVS / C2_SUB;
+
+template <bool IS_RESET>
+__global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);                     // [2][32][261]
+    float *s_tail = tiles + 2 * C2_SUB * OBS;                               // [256][11]
+    float *s_inv = s_tail + C2_ENVS * 11;                                   // [256]
+    double *s_invd = reinterpret_cast<double *>(s_inv + C2_ENVS);           // [256]
+
+    const int tid = threadIdx.x;
+    const long long n = a.n;
+    const long long first = (long long)blockIdx.x * C2_ENVS;
+    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
+    const int oldest = head + 1 == HIST ? 0 : head + 1;
+
+    // ------------------------------------------------------------------------------------------- phase 1
+    bool ended = false;
+    double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
+    {
+        const long long env = first + tid;
+        if (env < n) {
+            double cash = a.st.scal[env], holdings = a.st.scal[n + env];
+            Market m;
+            m.trend = a.st.scal[2 * n + env];
+            m.psych = a.st.scal[3 * n + env];
+            const uint32_t meta = a.st.meta[env];
+            int step = meta & 0xFFFF;
+            m.regime = (meta >> 16) & 0xFF;
+            uint32_t flags = meta >> 24;
+            uint32_t ctr = a.st.meta[n + env];
+            double ep_ret = a.st.ep_return[env];
+            bool selected = true;
+            if constexpr (IS_RESET) {
+                if (a.mask) selected = a.mask[env] != 0;
+                if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
+                    m.regime = SIDEWAYS;
+                    m.trend = 0.0;
+                    m.psych = 0.5;
+                    ctr = 0;
+                }
+            }
+            EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
+            double rew = 0.0, value = 0.0, price_out = 0.0, cur = 0.0;
+            int term = 0, trade = 0;
+            bool rewrote = false;
+
+            auto do_reset = [&]() {
+                cash = a.p.initial_balance;
+                holdings = 0.0;
+                step = 0;
+                flags = 0;
+                ep_ret = 0.0;
+                const WarmupResult wr = warmup_window(a.st.close, a.st.ohlv, n, env, head, a.p, m,
+                                                      a.p.env_id_base + (uint64_t)env, rng.ctr);
+                m = wr.m;
+                rng = EnvStream(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, wr.ctr);
+                rewrote = true;
+            };
+
+            if constexpr (IS_RESET) {
+                if (selected) do_reset();
+                else rewrote = true;  // (just re-read the newest close below)
+            } else {
+                if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
+                    do_reset();  // the ring head moved by one slot with this call: whole window at the new rotation
+                    price_out = a.st.close[(long long)head * n + env];
+                    value = cash + holdings * price_out;
+                } else {
+                    // _execute_action, :400-447
+                    const double price = a.st.close[(long long)a.p.window_head * n + env];
+                    const double initial_value = cash + holdings * price;
+                    if (a.p.action_type == 1) {
+                        const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
+                        const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
+                        const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
+                        if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
+                        else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
+                    } else {
+                        const long long act = reinterpret_cast<const long long *>(a.actions)[env];
+                        if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
+                        else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
+                        else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
+                        else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
+                        // anything else is a hold: the reference does not validate (:424-436)
+                    }
+                    const double final_value = cash + holdings * price;
+                    rew = final_value - initial_value;  // valued at the OLD price, :440-441
+                    if (!trade) rew -= 1.0;             // :444-445
+                    // next candle, :348-365
+                    const double volume = rng.uniform(0.5, 2.0);
+                    const double new_price = next_price(a.p, m, rng, price, volume);
+                    const double high = new_price * rng.uniform(1.0, 1.02);
+                    const double low = new_price * rng.uniform(0.98, 1.0);
+                    store_candle(a.st.close, a.st.ohlv, n, env, head, price, high, low, new_price, volume);
+                    cur = new_price;
+                    value = cash + holdings * new_price;
+                    price_out = new_price;
+                    step = min(step + 1, 65535);
+                    term = (step >= a.p.max_steps) || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
+                    ep_ret += rew;
+                    if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
+                        ended = true;
+                        st_ret = ep_ret;
+                        st_len = (double)step;
+                        st_val = value;
+                        if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
+                        if (a.io.ep_length) a.io.ep_length[env] = step;
+                        if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
+                        else flags |= CFLAG_NEEDS_RESET;
+                    }
+                }
+            }
+            if (rewrote) cur = a.st.close[(long long)head * n + env];  // same-thread read-after-write
+
+            // indicator features 250..260; the 49 older closes come straight from global memory
+            const double *cbase = a.st.close + env;
+            compose_indicators<false>(
+                a.p,
+                [&](int k) {
+                    int slot = oldest + k;
+                    slot = slot >= HIST ? slot - HIST : slot;
+                    return cbase[(long long)slot * n];
+                },
+                cur, cash, holdings, m.psych, nullptr, s_tail + tid * 11);
+            const double inv = 1.0 / cur;
+            s_invd[tid] = inv;
+            s_inv[tid] = (float)inv;
+
+            a.st.scal[env] = cash;
+            a.st.scal[n + env] = holdings;
+            a.st.scal[2 * n + env] = m.trend;
+            a.st.scal[3 * n + env] = m.psych;
+            a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
+            a.st.meta[n + env] = rng.ctr;
+            a.st.ep_return[env] = ep_ret;
+            if constexpr (!IS_RESET) {
+                a.io.reward[env] = (float)rew;
+                a.io.terminated[env] = (uint8_t)term;
+                if (a.io.truncated) a.io.truncated[env] = 0;
+                if (a.io.reward64) a.io.reward64[env] = rew;
+                if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
+                if (a.io.current_price) a.io.current_price[env] = price_out;
+                if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
+            }
+        }
+        if constexpr (!IS_RESET) {
+            if (a.io.stats) {
+                const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+                if (done_mask) {  // rare: ~1 step in 1000
+                    const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
+                    if ((tid & 31) == 0) {
+                        atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
+                        atomicAdd(&a.io.stats[1], r);
+                        atomicAdd(&a.io.stats[2], l);
+                        atomicAdd(&a.io.stats[3], v2);
+                    }
+                }
+            }
+        }
+    }
+    __threadfence();  // this step's candle (and a reset's whole window) must be in L2 before phase 2 reads it
+    __syncthreads();
+
+    // ------------------------------------------------------------------------------------------- phase 2
+    const int e = tid % C2_SUB, g = tid / C2_SUB;
+    constexpr int PER = (HIST + C2_GROUPS - 1) / C2_GROUPS;  // 7 slots per thread
+    // Element offsets of this thread's slots (they do not depend on the sub-tile; only the env column moves).
+    long long ooff[PER], coff[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int slot = oldest + g + C2_GROUPS * i;
+        slot = slot >= HIST ? slot - HIST : slot;
+        ooff[i] = (long long)slot * 4 * n;
+        coff[i] = (long long)slot * n;
+    }
+    // Software pipeline over the sub-tiles: the 35 window values of sub-tile s+1 are requested before sub-tile s is
+    // fenced, barriered and handed to the copy engine, so their latency overlaps that hand-over.
+    float x[PER][4], xn[PER][4];
+    double c[PER], cn[PER];
+    auto fetch = [&](int sub, float (&xo)[PER][4], double (&co)[PER]) {
+        const long long env = first + (long long)sub * C2_SUB + e;
+        if (sub < C2_GROUPS && env < n) {
+            const float *obase = a.st.ohlv + env;
+            const double *cbase = a.st.close + env;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                if (g + C2_GROUPS * i < HIST) {
+                    const float *o = obase + ooff[i];
+                    xo[i][0] = ld_cg_f32(o);
+                    xo[i][1] = ld_cg_f32(o + n);
+                    xo[i][2] = ld_cg_f32(o + 2 * n);
+                    xo[i][3] = ld_cg_f32(o + 3 * n);
+                    co[i] = ld_cg_f64(cbase + coff[i]);
+                }
+            }
+        }
+    };
+    fetch(0, x, c);
+#pragma unroll 1
+    for (int sub = 0; sub < C2_GROUPS; ++sub) {
+        const long long sub_first = first + (long long)sub * C2_SUB;
+        if (sub_first >= n) break;  // CTA-uniform
+        float *tile = tiles + (sub & 1) * (C2_SUB * OBS);
+        const long long env = sub_first + e;
+        const int le = sub * C2_SUB + e;  // env index within the CTA
+        if (sub >= 2) {  // the bulk copy that used this buffer two sub-tiles ago must have read it
+            if (tid == 0) bulk_wait_read<1>();
+            __syncthreads();
+        }
+        if (env < n) {
+            const float inv_f = s_inv[le];
+            const double inv_d = s_invd[le];
+            float *dst = tile + e * OBS;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int k = g + C2_GROUPS * i;
+                if (k < HIST) {
+                    dst[k * 5 + 0] = x[i][0] * inv_f;  // price_data / current_price, :513-515
+                    dst[k * 5 + 1] = x[i][1] * inv_f;
+                    dst[k * 5 + 2] = x[i][2] * inv_f;
+                    dst[k * 5 + 3] = (float)(c[i] * inv_d);
+                    dst[k * 5 + 4] = x[i][3] * inv_f;
+                }
+            }
+            // the 11 indicator features: groups 0..7 copy them (11 values over 8 groups)
+            for (int j = g; j < 11; j += C2_GROUPS) dst[250 + j] = s_tail[le * 11 + j];
+        }
+        fetch(sub + 1, xn, cn);  // next sub-tile's loads go out before the hand-over below
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const long long n_here = min((long long)C2_SUB, n - sub_first);
+            const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
+            const uint32_t bulk = bytes & ~15u;
+            if (bulk) bulk_store_s2g(a.io.obs + sub_first * OBS, tile, bulk);
+            bulk_commit();
+            for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[sub_first * OBS + i] = tile[i];  // ragged tail
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            x[i][0] = xn[i][0]; x[i][1] = xn[i][1]; x[i][2] = xn[i][2]; x[i][3] = xn[i][3];
+            c[i] = cn[i];
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
+constexpr size_t crypto2_smem_bytes() {
+    return (size_t)2 * C2_SUB * OBS * sizeof(float) + (size_t)C2_ENVS * 11 * sizeof(float) + C2_ENVS * sizeof(float) +
+           C2_ENVS * sizeof(double);
+}
+
 constexpr int CRYPTO_T = 32;  // envs per CTA (128 threads): 33.4 KB obs tile + 12.5 KB close staging, 4 CTAs per SM
 
 template <int T>
@@ -528,7 +808,15 @@ int launch(const CArgs &a, cudaStream_t stream) {
         tile_env = 0;
         if (const char *e = getenv("BENG_CRYPTO_TILE")) tile_env = atoi(e);
     }
-    const int T = tile_env > 0 ? tile_env : CRYPTO_T;
+    if (tile_env <= 0) {  // default: the two-phase kernel; BENG_CRYPTO_TILE=32|64|128 selects the warp-specialised one
+        const size_t smem = crypto2_smem_bytes();
+        auto kern = crypto2_kernel<IS_RESET>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<(unsigned)((a.n + C2_ENVS - 1) / C2_ENVS), C2_ENVS, smem, stream>>>(a);
+        return finish_launch();
+    }
+    const int T = tile_env;
 #define BENG_CCASE(TT)                                                                                          \
     if (T == TT) {                                                                                              \
         const size_t smem = crypto_smem_bytes<TT>();                                                            \
