@@ -22,7 +22,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Discrete, batch_space
-from .vector import AUTORESET_MODES, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
+from .vector import AUTORESET_MODES, LazyInfos as _LazyInfos, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
 
 HISTORY = 50
 OBS_DIM = 261
@@ -41,25 +41,6 @@ class TradingConfig:
     max_price: float = 100000.0
     volatility_base: float = 0.02
     market_psychology_factor: float = 0.1
-
-
-class _LazyInfos(dict):
-    """infos dict whose derived entries are computed on access (no per-step kernels for values nobody reads)."""
-
-    def __init__(self, *a, **k):
-        super().__init__(*a, **k)
-        self.lazy = {}
-
-    def __missing__(self, key):
-        if key in self.lazy:
-            return self.lazy[key]()
-        raise KeyError(key)
-
-    def __contains__(self, key):
-        return super().__contains__(key) or key in self.lazy
-
-    def keys(self):
-        return list(super().keys()) + list(self.lazy)
 
 
 class BatchedCryptoTradingEnv(_VectorEnvBase):

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/beng.h"
 
@@ -41,6 +42,30 @@ __device__ __forceinline__ void bulk_wait() {
 }
 // Make generic-proxy writes to shared memory visible to the async proxy (the copy engine).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// A step kernel depends on the previous step's state writes.  Launched with programmatic stream serialization, its
+// CTAs may become resident while the previous grid drains; everything before pdl_wait() (index math, shared-memory
+// setup) overlaps that tail, and pdl_wait() returns once the previous grid has completed and flushed its memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Launch `kern<<<grid, block, smem, stream>>>(arg)` with the PDL attribute (BENG_NO_PDL=1 disables it).
+template <typename Kern, typename Arg>
+inline cudaError_t launch_pdl(Kern kern, dim3 grid, dim3 block, size_t smem, cudaStream_t stream, const Arg &arg) {
+    static const bool use_pdl = getenv("BENG_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, arg);
+}
 
 // streaming (evict-first) 128-bit / 64-bit global loads for read-once inputs
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {

@@ -189,6 +189,10 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
     const long long n_tiles = (a.n_envs + T - 1) / T;
 
     if (tid < 5) s_stats[tid] = (tid == 4) ? INT_MIN : 0;
+    // PDL: let the next step's grid start becoming resident as this one drains, then wait for the PREVIOUS step's
+    // grid to have completed and flushed before touching anything it wrote (state, counters).
+    pdl_launch_dependents();
+    pdl_wait();
     if (blockIdx.x == 0 && tid == 0 && a.io.done_count_next) *a.io.done_count_next = 0;  // for the NEXT step
     __syncthreads();
 
@@ -496,8 +500,9 @@ int launch_one(const Args &a, const Config &c, cudaStream_t stream) {
     const long long n_tiles = (a.n_envs + T - 1) / T;
     long long grid = (long long)device_sm_count() * c.ctas_per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    kern<<<(unsigned)grid, T, smem, stream>>>(a);
-    return finish_launch();
+    e = launch_pdl(kern, dim3((unsigned)grid), dim3(T), smem, stream, a);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)e;
 }
 
 template <bool IS_RESET>

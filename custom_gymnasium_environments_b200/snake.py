@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Discrete, batch_space
-from .vector import AUTORESET_MODES, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
+from .vector import AUTORESET_MODES, LazyInfos, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
 
 STAT_NAMES = ("n_episodes", "sum_return", "sum_length", "sum_score", "max_score")
 
@@ -35,7 +35,8 @@ class BatchedSnakeEnv(_VectorEnvBase):
     metadata = {"render_modes": ["rgb_array"], "render_fps": 10, "autoreset_mode": "same_step"}
 
     def __init__(self, num_envs: int, grid_size: int = 20, render_mode=None, *, device="cuda", seed: int = 0,
-                 env_id_base: int = 0, autoreset_mode="same_step", max_steps: int = 1000, debug_checks: bool = False):
+                 env_id_base: int = 0, autoreset_mode="same_step", max_steps: int = 1000, debug_checks: bool = False,
+                 materialize_info: bool = False):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.num_envs = int(num_envs)
@@ -45,6 +46,10 @@ class BatchedSnakeEnv(_VectorEnvBase):
         self.autoreset_mode = _mode_name(autoreset_mode)
         self.metadata = dict(type(self).metadata, autoreset_mode=self.autoreset_mode)
         self.debug_checks = bool(debug_checks)
+        # info["score"] / info["snake_length"] are derivable from the state record (score == length - 1).  By default
+        # they are computed on access instead of being written to HBM every step (8 B per env-step);
+        # materialize_info=True makes the kernel write them (the host-buffer path always does).
+        self.materialize_info = bool(materialize_info)
         self.closed = False
 
         G, n, dev = self.grid_size, self.num_envs, self.device
@@ -64,8 +69,8 @@ class BatchedSnakeEnv(_VectorEnvBase):
             self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
             self.terminated = torch.zeros(n, dtype=torch.bool, device=dev)
             self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)
-            self.score = torch.zeros(n, dtype=torch.int32, device=dev)
-            self.snake_length = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._score = torch.zeros(n, dtype=torch.int32, device=dev)
+            self._snake_length = torch.zeros(n, dtype=torch.int32, device=dev)
             self.ep_return = torch.zeros(n, dtype=torch.float32, device=dev)
             self.ep_length = torch.zeros(n, dtype=torch.int32, device=dev)
             self.ep_score = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -78,31 +83,52 @@ class BatchedSnakeEnv(_VectorEnvBase):
             self.stats[4] = torch.iinfo(torch.int64).min
         self._state = _lib.SnakeState(self._core.data_ptr(), self._ring.data_ptr())
         self._ios = [self._make_io(self.obs, 0), self._make_io(self.obs, 1)]
+        self._ios_full = [self._make_io(self.obs, 0, True), self._make_io(self.obs, 1, True)]
+        self._info_fresh = True
         self._host = None
         self._needs_first_reset = True
 
     # ------------------------------------------------------------------ plumbing
-    def _make_io(self, obs: torch.Tensor, parity: int) -> "_lib.SnakeIO":
+    def _make_io(self, obs: torch.Tensor, parity: int, with_info: bool | None = None) -> "_lib.SnakeIO":
         cnt = self._done_counts.data_ptr()
+        info = self.materialize_info if with_info is None else with_info
         return _lib.SnakeIO(obs.data_ptr(), self.reward.data_ptr(), self.terminated.data_ptr(),
-                            self.truncated.data_ptr(), self.score.data_ptr(), self.snake_length.data_ptr(),
+                            self.truncated.data_ptr(), self._score.data_ptr() if info else None,
+                            self._snake_length.data_ptr() if info else None,
                             self.ep_return.data_ptr(), self.ep_length.data_ptr(), self.ep_score.data_ptr(),
                             cnt + 4 * parity, self.done_env.data_ptr(), cnt + 4 * (1 - parity),
                             self.stats.data_ptr(), self.invalid_count.data_ptr())
 
-    def _next_io(self):
+    def _next_io(self, full: bool = False):
         """The io block of this step; the two finished-env counters alternate (the kernel zeroes the other)."""
         self._parity ^= 1
-        return self._ios[self._parity]
+        self._info_fresh = full or self.materialize_info
+        return (self._ios_full if full else self._ios)[self._parity]
+
+    @property
+    def snake_length(self) -> torch.Tensor:
+        """info["snake_length"] of every env (int32), from the kernel's output or derived from the state record."""
+        if self._info_fresh:
+            return self._snake_length
+        return (self._core[:, 1] >> 16) & 0xFFFF
+
+    @property
+    def score(self) -> torch.Tensor:
+        """info["score"]: always length - 1 (snake_env.py:57,102 vs :97,107)."""
+        if self._info_fresh:
+            return self._score
+        return self.snake_length - 1
 
     @property
     def done_count(self) -> torch.Tensor:
         return self._done_counts[self._parity:self._parity + 1]
 
     def _infos(self):
-        return {"score": self.score, "snake_length": self.snake_length,
-                "episode": {"r": self.ep_return, "l": self.ep_length, "score": self.ep_score},
-                "_episode": self.terminated}
+        info = LazyInfos({"episode": {"r": self.ep_return, "l": self.ep_length, "score": self.ep_score},
+                          "_episode": self.terminated})
+        info.lazy["score"] = lambda: self.score
+        info.lazy["snake_length"] = lambda: self.snake_length
+        return info
 
     # ------------------------------------------------------------------ VectorEnv API
     def reset(self, *, seed=None, options=None):
@@ -126,11 +152,12 @@ class BatchedSnakeEnv(_VectorEnvBase):
             if self._needs_first_reset:
                 raise RuntimeError("the first reset() must reset every env")
         with torch.cuda.device(self.device):
-            rc = self.lib.beng_snake_reset(C.byref(self.params), C.byref(self._state), C.byref(self._ios[0]), mask_ptr,
+            self._info_fresh = True
+            rc = self.lib.beng_snake_reset(C.byref(self.params), C.byref(self._state), C.byref(self._ios_full[0]), mask_ptr,
                                            self.num_envs, int(first), stream_ptr(self.device))
         _lib.check(rc, "beng_snake_reset")
         self._needs_first_reset = False
-        return self.obs, {"score": self.score, "snake_length": self.snake_length}
+        return self.obs, {"score": self._score, "snake_length": self._snake_length}
 
     def step(self, actions, out_obs: torch.Tensor | None = None):
         """One step of every env (snake_env.py:67-119) -> (obs, rewards, terminations, truncations, infos).
@@ -193,7 +220,7 @@ class BatchedSnakeEnv(_VectorEnvBase):
             h["actions"].copy_(src.reshape(self.num_envs))
         with torch.cuda.device(self.device):
             rc = self.lib.beng_snake_step_host(
-                C.byref(self.params), C.byref(self._state), self._actions.data_ptr(), C.byref(self._next_io()),
+                C.byref(self.params), C.byref(self._state), self._actions.data_ptr(), C.byref(self._next_io(True)),
                 self.num_envs, h["actions"].data_ptr(), h["obs"].data_ptr() if copy_obs else None,
                 h["reward"].data_ptr(), h["terminated"].data_ptr(), h["truncated"].data_ptr(),
                 h["score"].data_ptr(), h["snake_length"].data_ptr(), stream_ptr(self.device))

@@ -60,3 +60,26 @@ def as_device_actions(actions, buf: torch.Tensor) -> torch.Tensor:
         raise ValueError(f"actions must have shape {tuple(buf.shape)}, got {arr.shape}")
     buf.copy_(torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)), non_blocking=False)
     return buf
+
+
+class LazyInfos(dict):
+    """infos dict whose derived entries are computed on access (no per-step kernels or HBM writes for values
+    nobody reads).  `lazy[key]` is a zero-argument callable returning the tensor."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.lazy = {}
+
+    def __missing__(self, key):
+        if key in self.lazy:
+            return self.lazy[key]()
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return super().__contains__(key) or key in self.lazy
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def keys(self):
+        return list(super().keys()) + list(self.lazy)
