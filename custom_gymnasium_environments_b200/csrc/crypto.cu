@@ -556,6 +556,8 @@ __global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
     const long long first = (long long)blockIdx.x * C2_ENVS;
     const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
     const int oldest = head + 1 == HIST ? 0 : head + 1;
+    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
+    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
 
     // ------------------------------------------------------------------------------------------- phase 1
     bool ended = false;
@@ -813,8 +815,9 @@ int launch(const CArgs &a, cudaStream_t stream) {
         auto kern = crypto2_kernel<IS_RESET>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)((a.n + C2_ENVS - 1) / C2_ENVS), C2_ENVS, smem, stream>>>(a);
-        return finish_launch();
+        e = launch_pdl(kern, dim3((unsigned)((a.n + C2_ENVS - 1) / C2_ENVS)), dim3(C2_ENVS), smem, stream, a);
+        g_launch_count.fetch_add(1, std::memory_order_relaxed);
+        return (int)e;
     }
     const int T = tile_env;
 #define BENG_CCASE(TT)                                                                                          \

@@ -102,6 +102,8 @@ __global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
     const long long first = (long long)blockIdx.x * T;
     const long long env = first + tid;
     const bool active = env < n;
+    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
+    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
 
     bool ended = false;
     double st_ret = 0.0, st_len = 0.0;
@@ -363,14 +365,15 @@ int launch(const TArgs &a, cudaStream_t stream) {
         auto kern = traffic_kernel<9, TRAFFIC_T, IS_RESET>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, TRAFFIC_T, smem, stream>>>(a);
+        e = launch_pdl(kern, dim3(grid), dim3(TRAFFIC_T), smem, stream, a);
     } else {
         auto kern = traffic_kernel<0, TRAFFIC_T, IS_RESET>;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<grid, TRAFFIC_T, smem, stream>>>(a);
+        e = launch_pdl(kern, dim3(grid), dim3(TRAFFIC_T), smem, stream, a);
     }
-    return finish_launch();
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)e;
 }
 
 int check(const beng_traffic_params *p, const beng_traffic_state *st, const beng_traffic_io *io, int64_t n) {
