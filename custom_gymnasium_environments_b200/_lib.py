@@ -14,7 +14,7 @@ _lib = None
 
 class SnakeParams(C.Structure):
     _fields_ = [("grid_size", C.c_int32), ("max_steps", C.c_int32), ("autoreset_mode", C.c_int32),
-                ("reserved", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+                ("time_limit_truncation", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
 
 
 class SnakeState(C.Structure):
@@ -31,8 +31,8 @@ class CryptoParams(C.Structure):
     _fields_ = [("initial_balance", C.c_double), ("trading_fee_rate", C.c_double), ("slippage_rate", C.c_double),
                 ("min_price", C.c_double), ("max_price", C.c_double), ("volatility_base", C.c_double),
                 ("market_psychology_factor", C.c_double), ("max_steps", C.c_int32), ("autoreset_mode", C.c_int32),
-                ("action_type", C.c_int32), ("window_head", C.c_int32), ("seed", C.c_uint64),
-                ("env_id_base", C.c_uint64)]
+                ("action_type", C.c_int32), ("window_head", C.c_int32), ("time_limit_truncation", C.c_int32),
+                ("reserved", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
 
 
 class CryptoState(C.Structure):
@@ -48,7 +48,8 @@ class CryptoIO(C.Structure):
 class TrafficParams(C.Structure):
     _fields_ = [("grid_rows", C.c_int32), ("grid_cols", C.c_int32), ("num_intersections", C.c_int32),
                 ("max_vehicles", C.c_int32), ("spawn_rate", C.c_double), ("max_timesteps", C.c_int32),
-                ("autoreset_mode", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+                ("autoreset_mode", C.c_int32), ("time_limit_truncation", C.c_int32), ("reserved", C.c_int32),
+                ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
 
 
 class TrafficState(C.Structure):

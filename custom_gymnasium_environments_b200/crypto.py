@@ -50,7 +50,8 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
 
     def __init__(self, num_envs: int, config: TradingConfig | None = None, action_type: str = "continuous",
                  render_mode=None, *, device="cuda", seed: int = 0, env_id_base: int = 0,
-                 autoreset_mode="same_step", max_steps: int = 1000, info_outputs: bool = True):
+                 autoreset_mode="same_step", max_steps: int = 1000, info_outputs: bool = True,
+                 time_limit_truncation: bool = False):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.num_envs = n = int(num_envs)
@@ -79,7 +80,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
         self.params = _lib.CryptoParams(c.initial_balance, c.trading_fee_rate, c.slippage_rate, c.min_price,
                                         c.max_price, c.volatility_base, c.market_psychology_factor, self.max_steps,
                                         AUTORESET_MODES[self.autoreset_mode], int(action_type == "continuous"),
-                                        0, int(seed), int(env_id_base))
+                                        0, int(bool(time_limit_truncation)), 0, int(seed), int(env_id_base))
         dev = self.device
         with torch.cuda.device(dev):
             z = lambda *shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731

@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
         float nw_o = 0.f, nw_h = 0.f, nw_l = 0.f, nw_v = 0.f;  // newest candle, float32 like the stored window
         Market m{SIDEWAYS, 0.0, 0.5};
         int step = 0, term = 0, trade = 0;
+        bool step_at_limit = false;
         uint32_t flags = 0, ctr = 0;
         bool reloaded = IS_RESET;
         if (active) {
@@ -444,7 +445,8 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
                     value = cash + holdings * new_price;
                     price_out = new_price;
                     step = min(step + 1, 65535);
-                    term = (step >= a.p.max_steps) || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
+                    step_at_limit = step >= a.p.max_steps;
+                    term = step_at_limit || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
                     ep_ret += rew;
                     if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
                         ended = true;
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
             if constexpr (!IS_RESET) {
                 a.io.reward[env] = (float)rew;
                 a.io.terminated[env] = (uint8_t)term;
-                if (a.io.truncated) a.io.truncated[env] = 0;
+                if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
                 if (a.io.reward64) a.io.reward64[env] = rew;
                 if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
                 if (a.io.current_price) a.io.current_price[env] = price_out;
@@ -588,6 +590,7 @@ __global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
             EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
             double rew = 0.0, value = 0.0, price_out = 0.0, cur = 0.0;
             int term = 0, trade = 0;
+            bool step_at_limit = false;
             bool rewrote = false;
 
             auto do_reset = [&]() {
@@ -642,7 +645,8 @@ __global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
                     value = cash + holdings * new_price;
                     price_out = new_price;
                     step = min(step + 1, 65535);
-                    term = (step >= a.p.max_steps) || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
+                    step_at_limit = step >= a.p.max_steps;
+                    term = step_at_limit || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
                     ep_ret += rew;
                     if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
                         ended = true;
@@ -682,7 +686,7 @@ __global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
             if constexpr (!IS_RESET) {
                 a.io.reward[env] = (float)rew;
                 a.io.terminated[env] = (uint8_t)term;
-                if (a.io.truncated) a.io.truncated[env] = 0;
+                if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
                 if (a.io.reward64) a.io.reward64[env] = rew;
                 if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
                 if (a.io.current_price) a.io.current_price[env] = price_out;

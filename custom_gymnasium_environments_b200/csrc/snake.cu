@@ -79,7 +79,7 @@ struct Args {
     beng_snake_io io;
     long long n_envs;
     uint64_t seed, env_id_base;
-    int G, max_steps, mode, first_call;
+    int G, max_steps, mode, first_call, tl_trunc;
 };
 
 // _place_food (snake_env.py:121-129): draw (row, col) until the cell is not part of the snake.
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
         bool ended = false;
         int ep_ret = 0, ep_len = 0, ep_score = 0;
         float rew = 0.0f;
-        int term = 0;
+        int term = 0, trunc = 0;
         bool invalid = false;
         Core s = unpack(cur.raw);
         if (active) {
@@ -316,7 +316,10 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
                             row[tail_cell] = 0;  // pop(), :107
                         }
                         s.steps = min(s.steps + 1, 65535);     // :109
-                        if (s.steps >= a.max_steps) term = 1;  // :112-114, reported as terminated
+                        if (s.steps >= a.max_steps) {
+                            term = 1;              // :112-114, reported as terminated
+                            trunc = a.tl_trunc;    // gym.make's TimeLimit would add truncated=True here
+                        }
                     }
                     if (term && a.mode != BENG_AUTORESET_DISABLED) {
                         ended = true;
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(T) snake_kernel(const Args a) {
             if constexpr (!IS_RESET) {
                 a.io.reward[env] = rew;
                 a.io.terminated[env] = (uint8_t)term;
-                if (a.io.truncated) a.io.truncated[env] = 0;  // never truncates, :119
+                if (a.io.truncated) a.io.truncated[env] = (uint8_t)trunc;  // raw class: never truncates, :119
                 if (invalid && a.io.invalid_count) atomicAdd(a.io.invalid_count, 1);
             }
             if (a.io.score) a.io.score[env] = s.length - 1;
@@ -541,6 +544,7 @@ Args make_args(const beng_snake_params *p, const beng_snake_state *st, const ben
     a.G = p->grid_size;
     a.max_steps = p->max_steps;
     a.mode = p->autoreset_mode;
+    a.tl_trunc = p->time_limit_truncation;
     return a;
 }
 

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
         if constexpr (!IS_RESET) {
             a.io.reward[env] = (float)rew;
             a.io.terminated[env] = (uint8_t)term;
-            if (a.io.truncated) a.io.truncated[env] = 0;  // :197
+            if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term);  // raw class: 0, :197
             if (a.io.reward64) a.io.reward64[env] = rew;
         }
     }

@@ -36,7 +36,7 @@ class BatchedSnakeEnv(_VectorEnvBase):
 
     def __init__(self, num_envs: int, grid_size: int = 20, render_mode=None, *, device="cuda", seed: int = 0,
                  env_id_base: int = 0, autoreset_mode="same_step", max_steps: int = 1000, debug_checks: bool = False,
-                 materialize_info: bool = False):
+                 materialize_info: bool = False, time_limit_truncation: bool = False):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.num_envs = int(num_envs)
@@ -58,7 +58,9 @@ class BatchedSnakeEnv(_VectorEnvBase):
         self.action_space = batch_space(self.single_action_space, n)
         self.observation_space = batch_space(self.single_observation_space, n)
 
-        self.params = _lib.SnakeParams(G, self.max_steps, AUTORESET_MODES[self.autoreset_mode], 0, int(seed),
+        # time_limit_truncation=True mirrors gym.make(): the TimeLimit wrapper ALSO reports truncated=True at max_steps
+        self.params = _lib.SnakeParams(G, self.max_steps, AUTORESET_MODES[self.autoreset_mode],
+                                       int(bool(time_limit_truncation)), int(seed),
                                        int(env_id_base))
         with torch.cuda.device(dev):
             # state (SoA)

@@ -41,7 +41,7 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
     def __init__(self, num_envs: int, grid_size=DEFAULT_GRID_SIZE, num_intersections: int = DEFAULT_NUM_INTERSECTIONS,
                  max_vehicles: int = MAX_VEHICLES, spawn_rate: float = DEFAULT_SPAWN_RATE, render_mode=None, *,
                  device="cuda", seed: int = 0, env_id_base: int = 0, autoreset_mode="same_step",
-                 max_timesteps: int = MAX_TIMESTEPS):
+                 max_timesteps: int = MAX_TIMESTEPS, time_limit_truncation: bool = False):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.num_envs = n = int(num_envs)
@@ -62,7 +62,8 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
 
         self.params = _lib.TrafficParams(self.grid_size[0], self.grid_size[1], int(num_intersections),
                                          self.max_vehicles, self.spawn_rate, int(max_timesteps),
-                                         AUTORESET_MODES[self.autoreset_mode], int(seed), int(env_id_base))
+                                         AUTORESET_MODES[self.autoreset_mode], int(bool(time_limit_truncation)), 0,
+                                         int(seed), int(env_id_base))
         dev = self.device
         with torch.cuda.device(dev):
             z = lambda *shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731

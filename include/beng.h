@@ -71,7 +71,10 @@ typedef struct beng_snake_params {
     int32_t grid_size;      /* `grid_size` ctor kwarg, default 20 (snake_env.py:19); 2..64 */
     int32_t max_steps;      /* `self.max_steps = 1000` (snake_env.py:47); 1..65535 */
     int32_t autoreset_mode; /* BENG_AUTORESET_* */
-    int32_t reserved;
+    int32_t time_limit_truncation; /* 0: `truncated` is always 0, like the raw reference class (snake_env.py:119).
+                                      1: ALSO set truncated on the step that reaches max_steps -- what gymnasium's
+                                      TimeLimit wrapper adds when the env is built with gym.make
+                                      (snake_env_classic/__init__.py:3-7, max_episode_steps=1000) */
     uint64_t seed;          /* key of the counter-based stream */
     uint64_t env_id_base;   /* global id of local env 0 */
 } beng_snake_params;
@@ -169,6 +172,9 @@ typedef struct beng_crypto_params {
     int32_t window_head;             /* slot (0..49) holding the NEWEST candle of every env before this call.
                                         A step writes the new candle to (window_head+1)%50 -- the caller then
                                         advances window_head by one; a reset leaves it unchanged. */
+    int32_t time_limit_truncation;   /* 1: also set `truncated` when current_step reaches max_steps (gym.make's
+                                        TimeLimit, crypto_trading_env.py:739-743); 0: never (raw class, :388) */
+    int32_t reserved;
     uint64_t seed;
     uint64_t env_id_base;
 } beng_crypto_params;
@@ -236,6 +242,9 @@ typedef struct beng_traffic_params {
     double spawn_rate;            /* default 0.3 */
     int32_t max_timesteps;        /* config.py:23 MAX_TIMESTEPS = 1000 */
     int32_t autoreset_mode;       /* BENG_AUTORESET_* */
+    int32_t time_limit_truncation; /* 1: also set `truncated` at max_timesteps (gym.make's TimeLimit,
+                                      traffic_management_env/__init__.py:7-17); 0: never (raw class, environment.py:197) */
+    int32_t reserved;
     uint64_t seed;
     uint64_t env_id_base;
 } beng_traffic_params;
