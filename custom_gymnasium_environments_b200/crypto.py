@@ -90,6 +90,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
             self._ep_return = z(n, dt=torch.float64)
             self._close = z(HISTORY, n, dt=torch.float64)
             self._ohlv = z(HISTORY, 4, n, dt=torch.float32)
+            self._scratch = z(12, n, dt=torch.float32)   # per-step hand-over between the two step kernels
             # outputs
             self.obs = z(n, OBS_DIM, dt=torch.float32)
             self.reward = z(n, dt=torch.float32)
@@ -104,7 +105,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
             self.stats = z(4, dt=torch.float64)
             self._actions = z(n, 2, dt=torch.float32) if action_type == "continuous" else z(n, dt=torch.int64)
         self._state = _lib.CryptoState(self._scal.data_ptr(), self._meta.data_ptr(), self._ep_return.data_ptr(),
-                                       self._close.data_ptr(), self._ohlv.data_ptr())
+                                       self._close.data_ptr(), self._ohlv.data_ptr(), self._scratch.data_ptr())
         ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self._io = _lib.CryptoIO(self.obs.data_ptr(), self.reward.data_ptr(), self.terminated.data_ptr(),
                                  self.truncated.data_ptr(), ptr(self.reward64), ptr(self.portfolio_value),

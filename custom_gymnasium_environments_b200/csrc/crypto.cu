@@ -800,6 +800,319 @@ constexpr size_t crypto2_smem_bytes() {
            C2_ENVS * sizeof(double);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Split step (BENG_CRYPTO_MODE=split; not the default, see launch()): two kernels, each shaped for what bounds it.
+//   crypto_dyn_kernel  one thread per env, no shared memory: trade, price walk, candle, termination, auto-reset and
+//                      the indicator scans (closes straight from global memory, coalesced over envs).  Leaves the 11
+//                      indicator features and 1/close in st.scratch [12][n].
+//   crypto_obs_kernel  persistent streaming kernel (like the snake step): per 32-env tile each thread fetches 35
+//                      window values one tile ahead, normalises them into one of three 33 KB tile buffers, and one
+//                      thread drains the tile with a bulk asynchronous copy.  Launched with PDL behind the first.
+template <int N, typename F>
+__device__ __forceinline__ double np_sum_stream(F val) {  // NumPy pairwise order for N in {14, 20}, values on demand
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = val(j);
+    if (N >= 16) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += val(8 + j);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int i = (N >= 16 ? 16 : 8); i < N; ++i) res += val(i);
+    return res;
+}
+
+template <bool IS_RESET>
+__global__ void __launch_bounds__(256, 2) crypto_dyn_kernel(const CArgs a) {
+    const long long n = a.n;
+    const long long env = (long long)blockIdx.x * 256 + threadIdx.x;
+    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
+    const int oldest = head + 1 == HIST ? 0 : head + 1;
+    pdl_launch_dependents();
+    pdl_wait();  // the previous step's observation kernel still reads the window slot this step overwrites
+
+    bool ended = false;
+    double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
+    if (env < n) {
+        double cash = a.st.scal[env], holdings = a.st.scal[n + env];
+        Market m;
+        m.trend = a.st.scal[2 * n + env];
+        m.psych = a.st.scal[3 * n + env];
+        const uint32_t meta = a.st.meta[env];
+        int step = meta & 0xFFFF;
+        m.regime = (meta >> 16) & 0xFF;
+        uint32_t flags = meta >> 24;
+        uint32_t ctr = a.st.meta[n + env];
+        double ep_ret = a.st.ep_return[env];
+        bool selected = true;
+        if constexpr (IS_RESET) {
+            if (a.mask) selected = a.mask[env] != 0;
+            if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
+                m.regime = SIDEWAYS;
+                m.trend = 0.0;
+                m.psych = 0.5;
+                ctr = 0;
+            }
+        }
+        EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
+        double rew = 0.0, value = 0.0, price_out = 0.0, cur = 0.0;
+        int term = 0, trade = 0;
+        bool step_at_limit = false, rewrote = false;
+
+        auto do_reset = [&]() {
+            cash = a.p.initial_balance;
+            holdings = 0.0;
+            step = 0;
+            flags = 0;
+            ep_ret = 0.0;
+            const WarmupResult wr = warmup_window(a.st.close, a.st.ohlv, n, env, head, a.p, m,
+                                                  a.p.env_id_base + (uint64_t)env, rng.ctr);
+            m = wr.m;
+            rng = EnvStream(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, wr.ctr);
+            rewrote = true;
+        };
+
+        if constexpr (IS_RESET) {
+            if (selected) do_reset();
+            else rewrote = true;  // (just re-read the newest close below)
+        } else {
+            if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
+                do_reset();  // the ring head moved by one slot with this call: whole window at the new rotation
+                price_out = a.st.close[(long long)head * n + env];
+                value = cash + holdings * price_out;
+            } else {
+                // _execute_action, :400-447
+                const double price = a.st.close[(long long)a.p.window_head * n + env];
+                const double initial_value = cash + holdings * price;
+                if (a.p.action_type == 1) {
+                    const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
+                    const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
+                    const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
+                    if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
+                    else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
+                } else {
+                    const long long act = reinterpret_cast<const long long *>(a.actions)[env];
+                    if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
+                    else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
+                    else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
+                    else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
+                    // anything else is a hold: the reference does not validate (:424-436)
+                }
+                const double final_value = cash + holdings * price;
+                rew = final_value - initial_value;  // valued at the OLD price, :440-441
+                if (!trade) rew -= 1.0;             // :444-445
+                // next candle, :348-365
+                const double volume = rng.uniform(0.5, 2.0);
+                const double new_price = next_price(a.p, m, rng, price, volume);
+                const double high = new_price * rng.uniform(1.0, 1.02);
+                const double low = new_price * rng.uniform(0.98, 1.0);
+                store_candle(a.st.close, a.st.ohlv, n, env, head, price, high, low, new_price, volume);
+                cur = new_price;
+                value = cash + holdings * new_price;
+                price_out = new_price;
+                step = min(step + 1, 65535);
+                step_at_limit = step >= a.p.max_steps;
+                term = step_at_limit || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
+                ep_ret += rew;
+                if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
+                    ended = true;
+                    st_ret = ep_ret;
+                    st_len = (double)step;
+                    st_val = value;
+                    if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
+                    if (a.io.ep_length) a.io.ep_length[env] = step;
+                    if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
+                    else flags |= CFLAG_NEEDS_RESET;
+                }
+            }
+        }
+        if (rewrote) cur = a.st.close[(long long)head * n + env];  // same-thread read-after-write
+
+        // ---- state, per-step outputs and the cheap features first: frees their registers for the scans below
+        float *sc = a.st.scratch + env;
+        {
+            const double cur_value = cash + holdings * cur;  // :519-527
+            sc[0] = (float)(cash / a.p.initial_balance);
+            sc[n] = (float)(holdings * cur / a.p.initial_balance);
+            sc[2 * n] = (float)(cur_value / a.p.initial_balance);
+            sc[10 * n] = (float)m.psych;        // :559
+            sc[11 * n] = (float)(1.0 / cur);    // hand-over to the observation kernel
+        }
+        a.st.scal[env] = cash;
+        a.st.scal[n + env] = holdings;
+        a.st.scal[2 * n + env] = m.trend;
+        a.st.scal[3 * n + env] = m.psych;
+        a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
+        a.st.meta[n + env] = rng.ctr;
+        a.st.ep_return[env] = ep_ret;
+        if constexpr (!IS_RESET) {
+            a.io.reward[env] = (float)rew;
+            a.io.terminated[env] = (uint8_t)term;
+            if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
+            if (a.io.reward64) a.io.reward64[env] = rew;
+            if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
+            if (a.io.current_price) a.io.current_price[env] = price_out;
+            if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
+        }
+
+        // ---- indicator scans over the 50 closes (oldest first); close k < 49 lives in slot (oldest + k) % 50.
+        // The last 20 closes stay in registers for the Bollinger / RSI windows: re-reading them through L1 with 1024
+        // threads per SM was measured 2x slower (L1 hit rate 41 %) than 512 threads with the window in registers.
+        const double *cbase = a.st.close + env;
+        float tail[11];
+        compose_indicators<false>(
+            a.p,
+            [&](int k) {
+                int slot = oldest + k;
+                slot = slot >= HIST ? slot - HIST : slot;
+                return cbase[(long long)slot * n];
+            },
+            cur, 0.0, 0.0, 0.0, nullptr, tail);
+#pragma unroll
+        for (int j = 3; j < 10; ++j) sc[(long long)j * n] = tail[j];  // RSI, MACD x3, Bollinger x3
+    }
+    if constexpr (!IS_RESET) {
+        if (a.io.stats) {
+            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+            if (done_mask) {  // rare: ~1 step in 1000
+                const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
+                if ((threadIdx.x & 31) == 0) {
+                    atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
+                    atomicAdd(&a.io.stats[1], r);
+                    atomicAdd(&a.io.stats[2], l);
+                    atomicAdd(&a.io.stats[3], v2);
+                }
+            }
+        }
+    }
+}
+
+constexpr int OBS_SUB = 32, OBS_THREADS = 256, OBS_GROUPS = OBS_THREADS / OBS_SUB, OBS_STAGES = 3;
+
+__global__ void __launch_bounds__(OBS_THREADS, 2) crypto_obs_kernel(const CArgs a, int head) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);  // [OBS_STAGES][32][261]
+    const int tid = threadIdx.x;
+    const int e = tid % OBS_SUB, g = tid / OBS_SUB;
+    const long long n = a.n;
+    const long long n_tiles = (n + OBS_SUB - 1) / OBS_SUB;
+    const int oldest = head + 1 == HIST ? 0 : head + 1;
+    constexpr int PER = (HIST + OBS_GROUPS - 1) / OBS_GROUPS;  // 7 slots per thread
+    long long ooff[PER], coff[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        int slot = oldest + g + OBS_GROUPS * i;
+        slot = slot >= HIST ? slot - HIST : slot;
+        ooff[i] = (long long)slot * 4 * n;
+        coff[i] = (long long)slot * n;
+    }
+    pdl_launch_dependents();
+    pdl_wait();  // everything below reads what the dynamics kernel of this step wrote
+
+    float x[PER][4], xn[PER][4], t0 = 0.f, t1 = 0.f, t0n = 0.f, t1n = 0.f, inv = 0.f, invn = 0.f;
+    double c[PER], cn[PER];
+    auto fetch = [&](long long tile, float (&xo)[PER][4], double (&co)[PER], float &ta, float &tb, float &iv) {
+        const long long env = tile * OBS_SUB + e;
+        if (tile < n_tiles && env < n) {
+            const float *obase = a.st.ohlv + env;
+            const double *cbase = a.st.close + env;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                if (g + OBS_GROUPS * i < HIST) {
+                    const float *o = obase + ooff[i];
+                    xo[i][0] = __ldg(o);
+                    xo[i][1] = __ldg(o + n);
+                    xo[i][2] = __ldg(o + 2 * n);
+                    xo[i][3] = __ldg(o + 3 * n);
+                    co[i] = __ldg(cbase + coff[i]);
+                }
+            }
+            const float *sc = a.st.scratch + env;
+            ta = __ldg(sc + (long long)g * n);                    // features 250 + g        (g = 0..7)
+            tb = (g < 3) ? __ldg(sc + (long long)(g + 8) * n) : 0.f;  // features 258, 259, 260  (g = 0..2)
+            iv = __ldg(sc + 11 * n);
+        }
+    };
+    fetch(blockIdx.x, x, c, t0, t1, inv);
+    int it = 0;
+#pragma unroll 1
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        float *buf = tiles + (size_t)(it % OBS_STAGES) * (OBS_SUB * OBS);
+        const long long first = tile * OBS_SUB;
+        const long long env = first + e;
+        fetch(tile + gridDim.x, xn, cn, t0n, t1n, invn);  // next tile's values, consumed next iteration
+        if (it >= OBS_STAGES) {  // the bulk copy that last used this buffer must have read it
+            if (tid == 0) bulk_wait_read<OBS_STAGES - 1>();
+            __syncthreads();
+        }
+        if (env < n) {
+            float *dst = buf + e * OBS;
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int k = g + OBS_GROUPS * i;
+                if (k < HIST) {
+                    dst[k * 5 + 0] = x[i][0] * inv;  // price_data / current_price, :513-515 (volume is divided too)
+                    dst[k * 5 + 1] = x[i][1] * inv;
+                    dst[k * 5 + 2] = x[i][2] * inv;
+                    dst[k * 5 + 3] = (float)(c[i] * (double)inv);
+                    dst[k * 5 + 4] = x[i][3] * inv;
+                }
+            }
+            dst[250 + g] = t0;
+            if (g < 3) dst[258 + g] = t1;
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const long long n_here = min((long long)OBS_SUB, n - first);
+            const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
+            const uint32_t bulk = bytes & ~15u;
+            if (bulk) bulk_store_s2g(a.io.obs + first * OBS, buf, bulk);
+            bulk_commit();
+            for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[first * OBS + i] = buf[i];  // ragged last tile
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            x[i][0] = xn[i][0]; x[i][1] = xn[i][1]; x[i][2] = xn[i][2]; x[i][3] = xn[i][3];
+            c[i] = cn[i];
+        }
+        t0 = t0n; t1 = t1n; inv = invn;
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
+template <bool IS_RESET>
+int launch_split(const CArgs &a, cudaStream_t stream) {
+    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
+    cudaError_t e = launch_pdl(crypto_dyn_kernel<IS_RESET>, dim3((unsigned)((a.n + 255) / 256)), dim3(256), 0, stream, a);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return (int)e;
+    const size_t smem = (size_t)OBS_STAGES * OBS_SUB * OBS * sizeof(float);
+    e = cudaFuncSetAttribute(crypto_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const long long n_tiles = (a.n + OBS_SUB - 1) / OBS_SUB;
+    long long grid = 2LL * device_sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    // (two-argument kernel: launch through the runtime's variadic form with the PDL attribute)
+    {
+        static const bool use_pdl = getenv("BENG_NO_PDL") == nullptr;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(OBS_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, crypto_obs_kernel, a, head);
+    }
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)e;
+}
+
 constexpr int CRYPTO_T = 32;  // envs per CTA (128 threads): 33.4 KB obs tile + 12.5 KB close staging, 4 CTAs per SM
 
 template <int T>
@@ -814,7 +1127,16 @@ int launch(const CArgs &a, cudaStream_t stream) {
         tile_env = 0;
         if (const char *e = getenv("BENG_CRYPTO_TILE")) tile_env = atoi(e);
     }
-    if (tile_env <= 0) {  // default: the two-phase kernel; BENG_CRYPTO_TILE=32|64|128 selects the warp-specialised one
+    // Default: the fused two-phase kernel (237 us/step at 262,144 envs).  BENG_CRYPTO_MODE=split selects the two-kernel
+    // step (277 us: its streaming observation kernel runs at 5.1 TB/s, but the stand-alone dynamics kernel loses the
+    // overlap it enjoys inside the fused kernel); BENG_CRYPTO_TILE=32|64|128 the warp-specialised kernel (381 us).
+    static int split = -1;
+    if (split < 0) {
+        const char *m = getenv("BENG_CRYPTO_MODE");
+        split = (m && m[0] == 's') ? 1 : 0;
+    }
+    if (split && a.st.scratch) return launch_split<IS_RESET>(a, stream);
+    if (tile_env <= 0) {
         const size_t smem = crypto2_smem_bytes();
         auto kern = crypto2_kernel<IS_RESET>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

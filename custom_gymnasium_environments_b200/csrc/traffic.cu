@@ -356,24 +356,27 @@ __global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
 
 constexpr int TRAFFIC_T = 64;  // envs (= threads) per CTA; 64 x 520 B = 33 KB observation tile
 
-template <bool IS_RESET>
-int launch(const TArgs &a, cudaStream_t stream) {
-    const size_t smem = (size_t)TRAFFIC_T * (a.ni * 14 + 4) * sizeof(float);
-    const unsigned grid = (unsigned)((a.n + TRAFFIC_T - 1) / TRAFFIC_T);
-    cudaError_t e;
-    if (a.ni == 9) {
-        auto kern = traffic_kernel<9, TRAFFIC_T, IS_RESET>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        e = launch_pdl(kern, dim3(grid), dim3(TRAFFIC_T), smem, stream, a);
-    } else {
-        auto kern = traffic_kernel<0, TRAFFIC_T, IS_RESET>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        e = launch_pdl(kern, dim3(grid), dim3(TRAFFIC_T), smem, stream, a);
-    }
+template <int NI_T, int T, bool IS_RESET>
+int launch_t(const TArgs &a, cudaStream_t stream) {
+    const size_t smem = (size_t)T * (a.ni * 14 + 4) * sizeof(float);
+    const unsigned grid = (unsigned)((a.n + T - 1) / T);
+    auto kern = traffic_kernel<NI_T, T, IS_RESET>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_pdl(kern, dim3(grid), dim3(T), smem, stream, a);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return (int)e;
+}
+
+template <bool IS_RESET>
+int launch(const TArgs &a, cudaStream_t stream) {
+    static int tile = -1;  // BENG_TRAFFIC_TILE=32|64 (read once; profiling sweeps)
+    if (tile < 0) {
+        const char *e = getenv("BENG_TRAFFIC_TILE");
+        tile = e ? atoi(e) : TRAFFIC_T;
+    }
+    if (a.ni == 9) return tile == 32 ? launch_t<9, 32, IS_RESET>(a, stream) : launch_t<9, 64, IS_RESET>(a, stream);
+    return launch_t<0, 64, IS_RESET>(a, stream);
 }
 
 int check(const beng_traffic_params *p, const beng_traffic_state *st, const beng_traffic_io *io, int64_t n) {

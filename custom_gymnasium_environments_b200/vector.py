@@ -83,3 +83,15 @@ class LazyInfos(dict):
 
     def keys(self):
         return list(super().keys()) + list(self.lazy)
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return super().__len__() + len(self.lazy)
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+    def values(self):
+        return [self[k] for k in self.keys()]
