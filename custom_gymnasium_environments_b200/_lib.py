@@ -61,6 +61,20 @@ class TrafficIO(C.Structure):
                                           "ep_length", "stats")]
 
 
+class ClimateParams(C.Structure):
+    _fields_ = [("max_occupancy", C.c_int32), ("episode_minutes", C.c_int32), ("autoreset_mode", C.c_int32),
+                ("time_limit_truncation", C.c_int32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64)]
+
+
+class ClimateState(C.Structure):
+    _fields_ = [("f64", C.c_void_p), ("i32", C.c_void_p)]
+
+
+class ClimateIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "terminated", "truncated", "reward64", "reward_terms",
+                                          "ep_return", "ep_length", "stats")]
+
+
 # name -> (restype, argtypes); also the list of symbols include/beng.h declares (tests check it).
 SIGNATURES = {
     "beng_version": (C.c_int, []),
@@ -90,6 +104,12 @@ SIGNATURES = {
                                     C.POINTER(TrafficIO), C.c_int64, C.c_void_p]),
     "beng_traffic_step_host": (C.c_int, [C.POINTER(TrafficParams), C.POINTER(TrafficState), C.c_void_p,
                                          C.POINTER(TrafficIO), C.c_int64] + [C.c_void_p] * 6),
+    "beng_climate_reset": (C.c_int, [C.POINTER(ClimateParams), C.POINTER(ClimateState), C.POINTER(ClimateIO),
+                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "beng_climate_step": (C.c_int, [C.POINTER(ClimateParams), C.POINTER(ClimateState), C.c_void_p, C.c_void_p,
+                                    C.POINTER(ClimateIO), C.c_int64, C.c_void_p]),
+    "beng_climate_step_host": (C.c_int, [C.POINTER(ClimateParams), C.POINTER(ClimateState), C.c_void_p, C.c_void_p,
+                                         C.POINTER(ClimateIO), C.c_int64] + [C.c_void_p] * 7),
     "beng_snake_export_state": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_int64] +
                                 [C.c_void_p] * 10),
 }

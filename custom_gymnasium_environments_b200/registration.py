@@ -16,6 +16,8 @@ def register_all():
         # crypto_trading_env/crypto_trading_env.py:739-743
         # traffic_management_env/__init__.py:7-17
         ("TrafficManagement-v0", "custom_gymnasium_environments_b200.traffic:TrafficManagementEnv", 1000),
+        # smartclimate_rl-main/smartclimate/__init__.py:6-10
+        ("SmartClimateEnv-v0", "custom_gymnasium_environments_b200.climate:SmartClimateEnv", 1440),
         ("CryptoTrading-v0", "custom_gymnasium_environments_b200.crypto:CryptoTradingEnv", 1000),
     ]
     for env_id, entry, max_steps in specs:

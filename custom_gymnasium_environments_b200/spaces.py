@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 try:  # pragma: no cover - depends on the environment
-    from gymnasium.spaces import Box, Discrete, MultiDiscrete  # type: ignore
+    from gymnasium.spaces import Box, Dict, Discrete, MultiBinary, MultiDiscrete  # type: ignore
 
     HAVE_GYMNASIUM = True
 except Exception:  # gymnasium absent
@@ -75,6 +75,43 @@ except Exception:  # gymnasium absent
             return (lo + (hi - lo) * self._rng.random(self.shape)).astype(self.dtype)
 
 
+if not HAVE_GYMNASIUM:
+
+    class MultiBinary(_Space):
+        def __init__(self, n):
+            super().__init__((int(n),), np.int8)
+            self.n = int(n)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(((x == 0) | (x == 1)).all())
+
+        def sample(self):
+            return (self._rng.random(self.shape) < 0.5).astype(np.int8)
+
+    class Dict:
+        """Minimal dictionary space (name -> space)."""
+
+        def __init__(self, spaces=None, **kw):
+            self.spaces = dict(spaces or {}, **kw)
+
+        def __getitem__(self, key):
+            return self.spaces[key]
+
+        def keys(self):
+            return self.spaces.keys()
+
+        def contains(self, x):
+            return isinstance(x, dict) and set(x) == set(self.spaces) and all(
+                sp.contains(x[k]) for k, sp in self.spaces.items())
+
+        def sample(self):
+            return {k: sp.sample() for k, sp in self.spaces.items()}
+
+        def __repr__(self):
+            return f"Dict({self.spaces!r})"
+
+
 def batch_space(space, n: int):
     """The batched counterpart of a single-env space (gymnasium.vector.utils.batch_space)."""
     if isinstance(space, Discrete):
@@ -84,4 +121,8 @@ def batch_space(space, n: int):
     if isinstance(space, Box):
         return Box(np.broadcast_to(space.low, (n,) + space.shape).copy(),
                    np.broadcast_to(space.high, (n,) + space.shape).copy(), dtype=space.dtype)
+    if isinstance(space, MultiBinary):
+        return Box(0, 1, (n,) + tuple(space.shape), np.int8)
+    if isinstance(space, Dict):
+        return Dict({k: batch_space(sp, n) for k, sp in space.spaces.items()})
     raise TypeError(f"cannot batch {space!r}")

@@ -294,6 +294,58 @@ int beng_traffic_step_host(const beng_traffic_params *p, const beng_traffic_stat
                            const beng_traffic_io *io, int64_t n_envs, const int64_t *actions_host, float *obs_host,
                            float *reward_host, uint8_t *terminated_host, uint8_t *truncated_host, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * smartclimate  (reference: smartclimate_rl-main/smartclimate/{env,utils}.py, class SmartClimateEnv)
+ * the simplest float env on the same engine / boundary.
+ * ------------------------------------------------------------------------------------------ */
+
+#define BENG_CLIMATE_OBS_DIM 9
+
+/* Constructor arguments (env.py:16-24) + batching parameters. */
+typedef struct beng_climate_params {
+    int32_t max_occupancy;         /* default 8 */
+    int32_t episode_minutes;       /* default 1440; reported as `terminated` (env.py:107); <= 65535 */
+    int32_t autoreset_mode;        /* BENG_AUTORESET_* */
+    int32_t time_limit_truncation; /* 1: also set `truncated` at episode_minutes (gym.make's TimeLimit,
+                                      smartclimate/__init__.py:6-10); 0: never (raw class, env.py:108) */
+    uint64_t seed;
+    uint64_t env_id_base;
+} beng_climate_params;
+
+/* Per-env state, [field][env] arrays (env index fastest).  float64 like the reference's Python floats. */
+typedef struct beng_climate_state {
+    double *f64;  /* [5][n] room_temp, outside_temp, ac_setting, total_reward, energy_usage */
+    int32_t *i32; /* [4][n] num_people | lights << 8 | flags << 16 ; current_step ; comfort_time ; rng_counter */
+} beng_climate_state;
+
+typedef struct beng_climate_io {
+    float *obs;           /* [n][9] room_temp, num_people, time_of_day, outside_temp, ac_setting, lights x4 (env.py:72-82) */
+    float *reward;        /* [n]    calculate_reward (utils.py:30-50) cast to float32 */
+    uint8_t *terminated;  /* [n]    current_step >= episode_minutes (env.py:107) */
+    uint8_t *truncated;   /* [n]    always 0 (env.py:108) unless time_limit_truncation */
+    double *reward64;     /* [n]    nullable */
+    double *reward_terms; /* [3][n] nullable: info["comfort"], ["ac_penalty"], ["light_penalty"] (utils.py:46-50) */
+    double *ep_return;    /* [n]    nullable, written when an episode ends (auto-reset modes) */
+    int32_t *ep_length;   /* [n]    nullable */
+    double *stats;        /* [3]    nullable running {n_episodes, sum_return, sum_length} */
+} beng_climate_io;
+
+/* SmartClimateEnv.reset / _init_state (env.py:48-70) for envs with mask[i] != 0 (NULL = all); first_call != 0 rewinds
+ * the rng counter.  The observation of EVERY env is written to io->obs. */
+int beng_climate_reset(const beng_climate_params *p, const beng_climate_state *st, const beng_climate_io *io,
+                       const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream);
+
+/* SmartClimateEnv.step (env.py:84-117) + utils.py:5-50 + auto-reset, ONE kernel launch.  The Dict action of the
+ * reference is passed as two arrays: ac_temp_dev float32 [n] (action['ac_temp'][0]) and lights_dev int8 [n][4]. */
+int beng_climate_step(const beng_climate_params *p, const beng_climate_state *st, const float *ac_temp_dev,
+                      const int8_t *lights_dev, const beng_climate_io *io, int64_t n_envs, void *stream);
+
+/* Same step with HOST action / result buffers; NULL host outputs are skipped; does not synchronise. */
+int beng_climate_step_host(const beng_climate_params *p, const beng_climate_state *st, float *ac_temp_dev,
+                           int8_t *lights_dev, const beng_climate_io *io, int64_t n_envs, const float *ac_temp_host,
+                           const int8_t *lights_host, float *obs_host, float *reward_host, uint8_t *terminated_host,
+                           uint8_t *truncated_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

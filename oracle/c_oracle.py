@@ -58,6 +58,13 @@ def lib():
         _lib.traffic_oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 8
         _lib.traffic_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 10
         _lib.traffic_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.climate_oracle_create.restype = C.c_void_p
+        _lib.climate_oracle_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
+        _lib.climate_oracle_destroy.argtypes = [C.c_void_p]
+        _lib.climate_oracle_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.climate_oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 12
+        _lib.climate_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
+        _lib.climate_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib.beng_oracle_draws_u32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.beng_oracle_action_tape.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_int,
                                                  C.c_void_p]
@@ -263,4 +270,56 @@ class TrafficOracle:
     def stats(self):
         out = np.zeros(3, np.float64)
         lib().traffic_oracle_get_stats(self._h, _p(out))
+        return dict(zip(["n_episodes", "sum_return", "sum_length"], out.tolist()))
+
+
+class ClimateOracle:
+    """Batched CPU oracle (float64) with the same outputs as the device engine's smartclimate step."""
+
+    def __init__(self, n_envs, max_occupancy=8, episode_minutes=1440, seed=0, env_id_base=0, autoreset="same_step"):
+        self.n = int(n_envs)
+        self._h = C.c_void_p(lib().climate_oracle_create(self.n, max_occupancy, episode_minutes, seed, env_id_base,
+                                                          AUTORESET[autoreset]))
+        n = self.n
+        self.obs = np.zeros((n, 9), np.float32)
+        self.reward = np.zeros(n, np.float32)
+        self.reward64 = np.zeros(n, np.float64)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+        self.comfort = np.zeros(n, np.float64)
+        self.ac_penalty = np.zeros(n, np.float64)
+        self.light_penalty = np.zeros(n, np.float64)
+        self.ep_return = np.zeros(n, np.float64)
+        self.ep_length = np.zeros(n, np.int32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().climate_oracle_destroy(self._h)
+            self._h = None
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().climate_oracle_reset(self._h, _p(m), _p(self.obs))
+        return self.obs
+
+    def step(self, ac_temp, lights):
+        a = np.ascontiguousarray(ac_temp, np.float32).reshape(self.n)
+        l = np.ascontiguousarray(lights, np.int8).reshape(self.n, 4)
+        lib().climate_oracle_step(self._h, _p(a), _p(l), _p(self.obs), _p(self.reward), _p(self.terminated),
+                                  _p(self.truncated), _p(self.reward64), _p(self.comfort), _p(self.ac_penalty),
+                                  _p(self.light_penalty), _p(self.ep_return), _p(self.ep_length))
+        return self.obs, self.reward, self.terminated, self.truncated
+
+    def state(self):
+        n = self.n
+        d = {"room_temp": np.zeros(n), "outside_temp": np.zeros(n), "total_reward": np.zeros(n),
+             "energy_usage": np.zeros(n), "num_people": np.zeros(n, np.int32), "current_step": np.zeros(n, np.int32),
+             "comfort_time": np.zeros(n, np.int32), "rng_counter": np.zeros(n, np.uint32)}
+        lib().climate_oracle_get_state(self._h, *[_p(d[k]) for k in ("room_temp", "outside_temp", "total_reward",
+                                       "energy_usage", "num_people", "current_step", "comfort_time", "rng_counter")])
+        return d
+
+    def stats(self):
+        out = np.zeros(3, np.float64)
+        lib().climate_oracle_get_stats(self._h, _p(out))
         return dict(zip(["n_episodes", "sum_return", "sum_length"], out.tolist()))

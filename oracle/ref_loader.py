@@ -81,3 +81,19 @@ def load_traffic():
     for n in ("config", "utils"):
         sys.modules.pop(n, None)
     return env_mod, utils_mod
+
+
+def load_climate():
+    """-> the reference module smartclimate_rl-main/smartclimate/env.py (class SmartClimateEnv).  The package's
+    __init__ registers with gymnasium and imports itself; only env.py and utils.py are needed, so they are loaded as
+    a synthetic package `_ref_smartclimate` (utils first: env.py does `from .utils import ...`)."""
+    if "_ref_smartclimate.env" in _cache:
+        return _cache["_ref_smartclimate.env"]
+    import types
+
+    d = os.path.join(REFERENCE_ROOT, "smartclimate_rl-main", "smartclimate")
+    pkg = types.ModuleType("_ref_smartclimate")
+    pkg.__path__ = [d]
+    sys.modules["_ref_smartclimate"] = pkg
+    _import_from(os.path.join(d, "utils.py"), "_ref_smartclimate.utils")
+    return _import_from(os.path.join(d, "env.py"), "_ref_smartclimate.env")

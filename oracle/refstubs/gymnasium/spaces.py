@@ -62,3 +62,16 @@ class Dict(Space):
     def __init__(self, spaces=None, **kw):
         super().__init__(None, None)
         self.spaces = dict(spaces or {}, **kw)
+
+
+class MultiBinary(Space):
+    def __init__(self, n):
+        super().__init__((int(n),), np.int8)
+        self.n = int(n)
+
+    def contains(self, x):
+        x = np.asarray(x)
+        return x.shape == self.shape and bool(((x == 0) | (x == 1)).all())
+
+    def sample(self):
+        return (np.random.random(self.shape) < 0.5).astype(np.int8)

@@ -84,3 +84,43 @@ class NumpyWithReplayNormal:
 
     def __getattr__(self, name):
         return getattr(np, name)
+
+
+class ReplayGenerator:
+    """Duck-types the subset of `numpy.random.Generator` that smartclimate uses (`self.rng` in
+    smartclimate_rl-main/smartclimate/env.py:31,49-52 and utils.py:5-24), backed by the engine's stream:
+
+      uniform(a, b)      = a + (b - a) * random53()                                  (2 u32)
+      integers(lo, hi)   = lo + mulhi(u32, hi - lo)            (hi exclusive)        (1 u32)
+      normal(mu, sd)     = Box-Muller on two random53()                              (4 u32)
+      choice(a, p=p)     = a[number of cdf entries <= random53()],  cdf = cumsum(p) / cumsum(p)[-1]   (2 u32)
+                           -- the inverse-CDF rule numpy's Generator.choice itself uses
+    """
+
+    def __init__(self, seed: int, env_id: int, start: int = 0):
+        self._rr = ReplayRandom(seed, env_id, start=start)
+
+    @property
+    def counter(self) -> int:
+        return self._rr.counter
+
+    def uniform(self, low=0.0, high=1.0):
+        return low + (high - low) * self._rr.random()
+
+    def integers(self, low, high=None):
+        if high is None:
+            low, high = 0, low
+        return int(low) + ((self._rr._u32() * (int(high) - int(low))) >> 32)
+
+    def normal(self, loc=0.0, scale=1.0):
+        return self._rr.normal(loc, scale)
+
+    def random(self):
+        return self._rr.random()
+
+    def choice(self, a, p=None):
+        if p is None:
+            return a[self.integers(0, len(a))]
+        cdf = np.asarray(p, dtype=np.float64).cumsum()
+        cdf /= cdf[-1]
+        return a[int(np.searchsorted(cdf, self._rr.random(), side="right"))]
