@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the batched env-step hot path (BASELINE.json: env-steps/sec; headline = batched SnakeEnv, 1M envs/GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--env snake|crypto|traffic]   # this repo's CUDA engine
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--env snake|crypto|traffic|climate]   # this repo's CUDA engine
     python bench.py --impl reference [--gpus N] --steps K --warmup W [--env …]  # CPU arm: the reference's step loop
 
 A "step" is ONE launch of the fused step kernel over the whole batch, inputs resident in HBM; `value` =
@@ -58,6 +58,11 @@ WORKLOADS = {
     "traffic": Workload("traffic", 1 << 16, 1210, 3, 9, "i32",
                         "batched TrafficManagementEnv, default config (9 intersections, 50 vehicles, spawn 0.3), "
                         "SAME_STEP auto-reset (BASELINE.json configs[3])", 520, 4 + 1 + 1, 600),
+    # SURVEY.md 8(f) rank 3 (no BASELINE config): state 5 x f64 + 4 x i32 read and written (112 + 112... = 80 + 32 each
+    # way), obs 36 W, action 8 R, reward 4 W, flags 2 W
+    "climate": Workload("climate", 1 << 20, 162, 2, 5, "f64",
+                        "batched SmartClimateEnv (SURVEY.md 8f rank 3), default config, random Dict actions, "
+                        "SAME_STEP auto-reset", 36, 4 + 1 + 1, 3000),
 }
 
 
@@ -82,6 +87,12 @@ def _cpu_worker_loop(args):
 
         np.random.seed(1234 + worker)
         env, n_act = CryptoPort(action_type="discrete"), 5
+    elif env_name == "climate":
+        import numpy as np
+
+        from oracle.climate_port import ClimatePort
+
+        env, n_act = ClimatePort(seed=1234 + worker), 2
     else:
         import numpy as np
 
@@ -91,7 +102,15 @@ def _cpu_worker_loop(args):
     env.reset()
     randrange = rng.randrange
     t0 = time.perf_counter()
-    if env_name == "traffic":
+    if env_name == "climate":
+        uniform = rng.uniform
+        for _ in range(n_steps):  # Dict action sample: ac_temp Box(16, 32, (1,)), lights MultiBinary(4)
+            act = {"ac_temp": np.array([uniform(16.0, 32.0)], dtype=np.float32),
+                   "lights": np.array([randrange(2) for _ in range(4)], dtype=np.int8)}
+            _, _, term, trunc, _ = env.step(act)
+            if term or trunc:
+                env.reset()
+    elif env_name == "traffic":
         for _ in range(n_steps):  # MultiDiscrete([3]*9) sample, like env.action_space.sample() in traffic test_env.py:266-278
             _, _, term, trunc, _ = env.step(np.array([randrange(3) for _ in range(9)]))
             if term or trunc:
@@ -134,6 +153,18 @@ def c_oracle_rate(env_name: str, seconds: float = 1.5) -> float:
         n = 1 << 11
         orc = c_oracle.CryptoOracle(n, seed=0)
         acts = rng.integers(0, 5, (16, n))
+    elif env_name == "climate":
+        n = 1 << 14
+        orc = c_oracle.ClimateOracle(n, seed=0)
+        ac = (rng.random((16, n)) * 16 + 16).astype(np.float32)
+        li = rng.integers(0, 2, (16, n, 4)).astype(np.int8)
+        orc.reset()
+        t0 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t0 < seconds:
+            orc.step(ac[k % 16], li[k % 16])
+            k += 1
+        return n * k / (time.perf_counter() - t0)
     else:
         n = 1 << 10
         orc = c_oracle.TrafficOracle(n, seed=0)
@@ -151,6 +182,7 @@ def c_oracle_rate(env_name: str, seconds: float = 1.5) -> float:
 def port_description(env_name, cores, per_proc):
     what = {"snake": "SnakeEnvClassic (oracle/snake_port.py), G=20",
             "crypto": "CryptoTradingEnv (oracle/crypto_port.py), discrete actions",
+            "climate": "SmartClimateEnv (oracle/climate_port.py), default config",
             "traffic": "TrafficManagementEnv (oracle/traffic_port.py; measured 1.5x FASTER than the real reference "
                        "in the build container, 2.9k vs 1.9k steps/s, so a conservative baseline), default config"
             }[env_name]
@@ -264,8 +296,10 @@ def workload_config(args, per_gpu):
               "over >= 64 distinct tensors")
     return {"workload": w.label, "env": w.name,
             "envs_per_gpu": per_gpu, "global_envs": per_gpu * args.gpus, "max_steps": 1000,
-            "actions": f"i.i.d. uniform{{0..{w.n_choices - 1}}} int64, device-generated tape (Philox stream 1), "
-                       "resident in HBM",
+            "actions": ("i.i.d. Dict actions (ac_temp ~ U(16, 32) float32, lights ~ Bernoulli(0.5) int8 x4), torch-generated "
+                        "tape resident in HBM") if w.name == "climate" else
+                       (f"i.i.d. uniform{{0..{w.n_choices - 1}}} int64, device-generated tape (Philox stream 1), "
+                        "resident in HBM"),
             "l2_policy": l2,
             "parallelism": f"env-sharded x{args.gpus}, no data-path collective"}
 
@@ -294,6 +328,8 @@ def make_env(pkg, env_name, n, dev, seed, base):
         return pkg.BatchedSnakeEnv(n, 20, device=dev, seed=seed, env_id_base=base)
     if env_name == "crypto":
         return pkg.BatchedCryptoTradingEnv(n, None, "discrete", device=dev, seed=seed, env_id_base=base)
+    if env_name == "climate":
+        return pkg.BatchedSmartClimateEnv(n, device=dev, seed=seed, env_id_base=base)
     return pkg.BatchedTrafficManagementEnv(n, device=dev, seed=seed, env_id_base=base)
 
 
@@ -308,6 +344,8 @@ def kernel_description(lib, env_name, n):
     if env_name == "crypto":
         return ("beng::crypto_kernel<T=32,IS_RESET=false>: 128-thread warp-specialised CTA per 32-env tile "
                 "(1 env warp + 3 window warps)")
+    if env_name == "climate":
+        return "beng::climate_kernel<T=256,IS_RESET=false>: one thread per env, 256-env tile per CTA"
     return "beng::traffic_kernel<NI=9,T=64,IS_RESET=false>: one thread per env, 64-env tile per CTA"
 
 
@@ -340,11 +378,19 @@ def run_b200_arm(args):
 
     # action tapes, resident in HBM before the timed region (pool of distinct steps, cycled)
     pool = max(64, min(args.steps + args.warmup, args.action_pool))
-    tape_shape = (pool, n) if w.n_cols == 1 else (pool, n, w.n_cols)
-    tapes = torch.empty(tape_shape, dtype=torch.int64, device=dev)
-    for t in range(pool):
-        pkg._lib.check(lib.beng_fill_random_actions(tapes[t].data_ptr(), n, w.n_cols, w.n_choices, t, base, seed,
-                                                    stream.cuda_stream), "beng_fill_random_actions")
+    if args.env == "climate":  # Dict action: ac_temp float32 (n,), lights int8 (n, 4), torch-generated tapes
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        ac_t = torch.rand((pool, n), device=dev, generator=gen) * 16.0 + 16.0
+        li_t = torch.randint(0, 2, (pool, n, 4), device=dev, generator=gen).to(torch.int8)
+        tapes = [{"ac_temp": ac_t[t], "lights": li_t[t]} for t in range(pool)]
+        to_host = lambda a: {k: v.cpu().pin_memory() for k, v in a.items()}  # noqa: E731
+    else:
+        tape_shape = (pool, n) if w.n_cols == 1 else (pool, n, w.n_cols)
+        tapes = torch.empty(tape_shape, dtype=torch.int64, device=dev)
+        for t in range(pool):
+            pkg._lib.check(lib.beng_fill_random_actions(tapes[t].data_ptr(), n, w.n_cols, w.n_choices, t, base, seed,
+                                                        stream.cuda_stream), "beng_fill_random_actions")
+        to_host = lambda a: a.cpu().pin_memory()  # noqa: E731
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -398,8 +444,8 @@ def run_b200_arm(args):
 
     # ---- end-to-end through the host-buffer C-ABI call -------------------------------------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    host_tapes = [tapes[t % pool].cpu().pin_memory() for t in range(min(e2e_steps + 2, 8))]
-    h2d = n * 8 * w.n_cols
+    host_tapes = [to_host(tapes[t % pool]) for t in range(min(e2e_steps + 2, 8))]
+    h2d = n * 8 if args.env == "climate" else n * 8 * w.n_cols
     d2h_full = n * (w.obs_bytes + w.result_bytes)
     d2h_lite = n * w.result_bytes
 
@@ -447,6 +493,7 @@ def run_b200_arm(args):
     achieved = n * w.bytes / (per_launch_ms * 1e-3) / 1e9
     api = {"snake": "BatchedSnakeEnv.step_host -> beng_snake_step_host",
            "crypto": "BatchedCryptoTradingEnv.step_host -> beng_crypto_step_host",
+           "climate": "BatchedSmartClimateEnv.step_host -> beng_climate_step_host",
            "traffic": "BatchedTrafficManagementEnv.step_host -> beng_traffic_step_host"}[args.env]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -494,7 +541,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--env", choices=sorted(WORKLOADS), default="snake",
-                    help="snake = the BASELINE.json headline (configs[1]); crypto = configs[2]; traffic = configs[3]")
+                    help="snake = the BASELINE.json headline (configs[1]); crypto = configs[2]; traffic = configs[3]; "
+                         "climate = SURVEY.md 8(f) rank 3 (no BASELINE config)")
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--action-pool", type=int, default=256, help="distinct pre-generated action steps kept in HBM")
     ap.add_argument("--e2e-steps", type=int, default=20)

@@ -164,8 +164,12 @@ class BatchedSmartClimateEnv(_VectorEnvBase):
                           "truncated": torch.zeros(n, dtype=torch.bool, **pin)}
         h = self._host
         ac, lights = self._split_action(actions)
-        h["ac"].copy_(torch.as_tensor(np.asarray(ac, dtype=np.float32)).reshape(-1))
-        h["lights"].copy_(torch.as_tensor(np.asarray(lights, dtype=np.int8)).reshape(-1, 4))
+        ac_src = ac if isinstance(ac, torch.Tensor) else torch.as_tensor(np.asarray(ac, dtype=np.float32))
+        li_src = lights if isinstance(lights, torch.Tensor) else torch.as_tensor(np.asarray(lights, dtype=np.int8))
+        if ac_src.data_ptr() != h["ac"].data_ptr():
+            h["ac"].copy_(ac_src.reshape(-1))
+        if li_src.data_ptr() != h["lights"].data_ptr():
+            h["lights"].copy_(li_src.reshape(-1, 4))
         with torch.cuda.device(self.device):
             rc = self.lib.beng_climate_step_host(
                 C.byref(self.params), C.byref(self._state), self._ac.data_ptr(), self._lights.data_ptr(),
