@@ -75,6 +75,21 @@ class ClimateIO(C.Structure):
                                           "ep_return", "ep_length", "stats")]
 
 
+class BuilderParams(C.Structure):
+    _fields_ = [("grid_size", C.c_int32), ("autoreset_mode", C.c_int32), ("seed", C.c_uint64),
+                ("env_id_base", C.c_uint64)]
+
+
+class BuilderState(C.Structure):
+    _fields_ = [("words", C.c_void_p)]
+
+
+class BuilderIO(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("grid", "resources", "capacity", "win_steps", "flat_obs", "reward",
+                                          "terminated", "truncated", "ep_return", "ep_length", "stats",
+                                          "invalid_count")]
+
+
 # name -> (restype, argtypes); also the list of symbols include/beng.h declares (tests check it).
 SIGNATURES = {
     "beng_version": (C.c_int, []),
@@ -110,6 +125,12 @@ SIGNATURES = {
                                     C.POINTER(ClimateIO), C.c_int64, C.c_void_p]),
     "beng_climate_step_host": (C.c_int, [C.POINTER(ClimateParams), C.POINTER(ClimateState), C.c_void_p, C.c_void_p,
                                          C.POINTER(ClimateIO), C.c_int64] + [C.c_void_p] * 7),
+    "beng_builder_reset": (C.c_int, [C.POINTER(BuilderParams), C.POINTER(BuilderState), C.POINTER(BuilderIO),
+                                     C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "beng_builder_step": (C.c_int, [C.POINTER(BuilderParams), C.POINTER(BuilderState), C.c_void_p,
+                                    C.POINTER(BuilderIO), C.c_int64, C.c_void_p]),
+    "beng_builder_step_host": (C.c_int, [C.POINTER(BuilderParams), C.POINTER(BuilderState), C.c_void_p,
+                                         C.POINTER(BuilderIO), C.c_int64] + [C.c_void_p] * 8),
     "beng_snake_export_state": (C.c_int, [C.POINTER(SnakeParams), C.POINTER(SnakeState), C.c_int64] +
                                 [C.c_void_p] * 10),
 }

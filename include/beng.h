@@ -346,6 +346,62 @@ int beng_climate_step_host(const beng_climate_params *p, const beng_climate_stat
                            const int8_t *lights_host, float *obs_host, float *reward_host, uint8_t *terminated_host,
                            uint8_t *truncated_host, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * world_builder_env  (reference: world_builder_env/src/environment/{world_builder_env,game_logic}.py)
+ * integer grid builder on the same engine / boundary.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Constructor arguments (world_builder_env.py:38-44) + batching parameters.  The game constants (costs, production,
+ * MAX_POPULATION 20, WIN_STEPS 50, initial resources) are compiled in (game_logic.py:13-57). */
+typedef struct beng_builder_params {
+    int32_t grid_size;      /* default 10; 2..15 */
+    int32_t autoreset_mode; /* BENG_AUTORESET_* */
+    uint64_t seed;
+    uint64_t env_id_base;
+} beng_builder_params;
+
+/* Per-env scalar state, [word][env] int32 array (env index fastest):
+ *   0 food  1 wood  2 stone  3 population  4 population_capacity
+ *   5 building counts: farm | lumberyard << 8 | quarry << 16 | house << 24
+ *   6 steps  7 win_steps | reached_win_population << 16 | flags << 24  8 rng_counter  9 running episode return
+ * The grid itself lives in io->grid: it is both state and observation (one cell changes per successful build). */
+typedef struct beng_builder_state {
+    int32_t *words; /* [10][n] */
+} beng_builder_state;
+
+typedef struct beng_builder_io {
+    int8_t *grid;            /* [n][G][G]  obs['grid'] AND the persistent grid state (0 empty, 1 farm, 2 lumberyard,
+                                           3 quarry, 4 house); read and rewritten in place by every step */
+    float *resources;        /* [n][4]     obs['resources'] = food, wood, stone, population (world_builder_env.py:205-210) */
+    float *capacity;         /* [n][1]     obs['population_capacity'] */
+    int32_t *win_steps;      /* [n][1]     obs['win_steps'] */
+    float *flat_obs;         /* [n][G*G+6] nullable: the flatten_obs=True observation (:189-200) */
+    float *reward;           /* [n]        execute_action's reward, or -100 / +100 on termination (:150-157) */
+    uint8_t *terminated;     /* [n]        population <= 0, or 50 steps at population >= 20 (:233-247) */
+    uint8_t *truncated;      /* [n]        always 0 (:148) */
+    int32_t *ep_return;      /* [n] nullable, written when an episode ends (auto-reset modes) */
+    int32_t *ep_length;      /* [n] nullable */
+    int64_t *stats;          /* [4] nullable running {n_episodes, sum_return, sum_length, wins} (integer, exact) */
+    int32_t *invalid_count;  /* [1] nullable: out-of-space actions seen (the reference raises ValueError, :135-136;
+                                    such an env is left untouched) */
+} beng_builder_io;
+
+/* WorldBuilderEnv.reset (world_builder_env.py:99-123) for envs with mask[i] != 0 (NULL = all); first_call != 0 rewinds the
+ * rng counter.  The observation of EVERY env is (re)written. */
+int beng_builder_reset(const beng_builder_params *p, const beng_builder_state *st, const beng_builder_io *io,
+                       const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream);
+
+/* WorldBuilderEnv.step (:125-166) + GameLogic.execute_action and helpers (game_logic.py:59-203) + auto-reset, ONE
+ * kernel launch.  actions_dev: int64 [n], 0 pass / 1 farm / 2 lumberyard / 3 quarry / 4 house. */
+int beng_builder_step(const beng_builder_params *p, const beng_builder_state *st, const int64_t *actions_dev,
+                      const beng_builder_io *io, int64_t n_envs, void *stream);
+
+/* Same step with HOST action / result buffers; NULL host outputs are skipped; does not synchronise. */
+int beng_builder_step_host(const beng_builder_params *p, const beng_builder_state *st, int64_t *actions_dev,
+                           const beng_builder_io *io, int64_t n_envs, const int64_t *actions_host, int8_t *grid_host,
+                           float *resources_host, float *capacity_host, int32_t *win_steps_host, float *reward_host,
+                           uint8_t *terminated_host, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

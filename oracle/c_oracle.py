@@ -65,6 +65,14 @@ def lib():
         _lib.climate_oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 12
         _lib.climate_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 8
         _lib.climate_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.builder_oracle_create.restype = C.c_void_p
+        _lib.builder_oracle_create.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int]
+        _lib.builder_oracle_destroy.argtypes = [C.c_void_p]
+        _lib.builder_oracle_reset.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        _lib.builder_oracle_step.restype = C.c_int
+        _lib.builder_oracle_step.argtypes = [C.c_void_p] + [C.c_void_p] * 10
+        _lib.builder_oracle_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        _lib.builder_oracle_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib.beng_oracle_draws_u32.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib.beng_oracle_action_tape.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int, C.c_int,
                                                  C.c_void_p]
@@ -323,3 +331,61 @@ class ClimateOracle:
         out = np.zeros(3, np.float64)
         lib().climate_oracle_get_stats(self._h, _p(out))
         return dict(zip(["n_episodes", "sum_return", "sum_length"], out.tolist()))
+
+
+class BuilderOracle:
+    """Batched CPU oracle with the same outputs as the device engine's world-builder step."""
+
+    def __init__(self, n_envs, grid_size=10, seed=0, env_id_base=0, autoreset="same_step"):
+        self.n, self.G = int(n_envs), int(grid_size)
+        self._h = C.c_void_p(lib().builder_oracle_create(self.n, self.G, seed, env_id_base, AUTORESET[autoreset]))
+        n, G = self.n, self.G
+        self.grid = np.zeros((n, G, G), np.int8)
+        self.resources = np.zeros((n, 4), np.float32)
+        self.capacity = np.zeros((n, 1), np.float32)
+        self.win_steps = np.zeros((n, 1), np.int32)
+        self.reward = np.zeros(n, np.float32)
+        self.terminated = np.zeros(n, np.uint8)
+        self.truncated = np.zeros(n, np.uint8)
+        self.ep_return = np.zeros(n, np.int32)
+        self.ep_length = np.zeros(n, np.int32)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().builder_oracle_destroy(self._h)
+            self._h = None
+
+    def obs(self):
+        return {"grid": self.grid, "resources": self.resources, "population_capacity": self.capacity,
+                "win_steps": self.win_steps}
+
+    def flat_obs(self):
+        return np.concatenate([self.grid.reshape(self.n, -1).astype(np.float32), self.resources, self.capacity,
+                               self.win_steps.astype(np.float32)], axis=1)
+
+    def reset(self, mask=None):
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().builder_oracle_reset(self._h, _p(m), _p(self.grid), _p(self.resources), _p(self.capacity),
+                                   _p(self.win_steps))
+        return self.obs()
+
+    def step(self, actions):
+        a = np.ascontiguousarray(actions, np.int64)
+        assert a.shape == (self.n,)
+        self.invalid = lib().builder_oracle_step(self._h, _p(a), _p(self.grid), _p(self.resources), _p(self.capacity),
+                                                 _p(self.win_steps), _p(self.reward), _p(self.terminated),
+                                                 _p(self.truncated), _p(self.ep_return), _p(self.ep_length))
+        return self.obs(), self.reward, self.terminated, self.truncated
+
+    def state(self):
+        n = self.n
+        d = {"steps": np.zeros(n, np.int32), "reached": np.zeros(n, np.int32), "rng_counter": np.zeros(n, np.uint32),
+             "building_counts": np.zeros((n, 4), np.int32)}
+        lib().builder_oracle_get_state(self._h, _p(d["steps"]), _p(d["reached"]), _p(d["rng_counter"]),
+                                       _p(d["building_counts"]))
+        return d
+
+    def stats(self):
+        out = np.zeros(4, np.int64)
+        lib().builder_oracle_get_stats(self._h, _p(out))
+        return dict(zip(["n_episodes", "sum_return", "sum_length", "wins"], out.tolist()))

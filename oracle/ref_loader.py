@@ -97,3 +97,20 @@ def load_climate():
     sys.modules["_ref_smartclimate"] = pkg
     _import_from(os.path.join(d, "utils.py"), "_ref_smartclimate.utils")
     return _import_from(os.path.join(d, "env.py"), "_ref_smartclimate.env")
+
+
+def load_builder():
+    """-> (world_builder_env module, game_logic module) of world_builder_env/src/environment.  The package's renderer
+    imports pygame at top level (stubbed); the modules are loaded as a synthetic package `_ref_builder`."""
+    if "_ref_builder.world_builder_env" in _cache:
+        return _cache["_ref_builder.world_builder_env"], _cache["_ref_builder.game_logic"]
+    import types
+
+    d = os.path.join(REFERENCE_ROOT, "world_builder_env", "src", "environment")
+    pkg = types.ModuleType("_ref_builder")
+    pkg.__path__ = [d]
+    sys.modules["_ref_builder"] = pkg
+    gl = _import_from(os.path.join(d, "game_logic.py"), "_ref_builder.game_logic")
+    _import_from(os.path.join(d, "renderer.py"), "_ref_builder.renderer")
+    env = _import_from(os.path.join(d, "world_builder_env.py"), "_ref_builder.world_builder_env")
+    return env, gl

@@ -124,3 +124,27 @@ class ReplayGenerator:
         cdf = np.asarray(p, dtype=np.float64).cumsum()
         cdf /= cdf[-1]
         return a[int(np.searchsorted(cdf, self._rr.random(), side="right"))]
+
+
+class NumpyWithReplayRandint:
+    """Stands in for the `np` name inside the reference's game_logic module: everything forwards to numpy except
+    `np.random.randint(n)` (world_builder_env/src/environment/game_logic.py:137), which becomes one draw of the
+    engine's stream: randint(n) = mulhi(u32, n)."""
+
+    class _Random:
+        def __init__(self, rr):
+            self._rr = rr
+
+        def randint(self, low, high=None):
+            if high is None:
+                low, high = 0, low
+            return self._rr.randint(int(low), int(high) - 1)
+
+        def seed(self, *_a, **_k):
+            pass
+
+    def __init__(self, rr):
+        self.random = self._Random(rr)
+
+    def __getattr__(self, name):
+        return getattr(np, name)
