@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the batched env-step hot path (BASELINE.json: env-steps/sec; headline = batched SnakeEnv, 1M envs/GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--env snake|crypto|traffic|climate]   # this repo's CUDA engine
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--env snake|crypto|traffic|climate|builder]   # this repo's CUDA engine
     python bench.py --impl reference [--gpus N] --steps K --warmup W [--env …]  # CPU arm: the reference's step loop
 
 A "step" is ONE launch of the fused step kernel over the whole batch, inputs resident in HBM; `value` =
@@ -63,6 +63,11 @@ WORKLOADS = {
     "climate": Workload("climate", 1 << 20, 162, 2, 5, "f64",
                         "batched SmartClimateEnv (SURVEY.md 8f rank 3), default config, random Dict actions, "
                         "SAME_STEP auto-reset", 36, 4 + 1 + 1, 3000),
+    # SURVEY.md 8(f) rank 3 (no BASELINE config): grid 100 R + 100 W (state = observation, rewritten in place),
+    # scalar state 40 R + 40 W, resources/capacity/win_steps 24 W, action 8 R, reward 4 W, flags 2 W
+    "builder": Workload("builder", 1 << 20, 318, 5, 1, "i32",
+                        "batched WorldBuilderEnv (SURVEY.md 8f rank 3), 10x10 grid, Dict observation, random actions, "
+                        "SAME_STEP auto-reset", 100 + 16 + 4 + 4, 4 + 1, 6000),
 }
 
 
@@ -87,6 +92,13 @@ def _cpu_worker_loop(args):
 
         np.random.seed(1234 + worker)
         env, n_act = CryptoPort(action_type="discrete"), 5
+    elif env_name == "builder":
+        import numpy as np
+
+        from oracle.builder_port import BuilderPort
+
+        np.random.seed(1234 + worker)
+        env, n_act = BuilderPort(), 5
     elif env_name == "climate":
         import numpy as np
 
@@ -153,6 +165,10 @@ def c_oracle_rate(env_name: str, seconds: float = 1.5) -> float:
         n = 1 << 11
         orc = c_oracle.CryptoOracle(n, seed=0)
         acts = rng.integers(0, 5, (16, n))
+    elif env_name == "builder":
+        n = 1 << 14
+        orc = c_oracle.BuilderOracle(n, seed=0)
+        acts = rng.integers(0, 5, (16, n))
     elif env_name == "climate":
         n = 1 << 14
         orc = c_oracle.ClimateOracle(n, seed=0)
@@ -183,6 +199,7 @@ def port_description(env_name, cores, per_proc):
     what = {"snake": "SnakeEnvClassic (oracle/snake_port.py), G=20",
             "crypto": "CryptoTradingEnv (oracle/crypto_port.py), discrete actions",
             "climate": "SmartClimateEnv (oracle/climate_port.py), default config",
+            "builder": "WorldBuilderEnv (oracle/builder_port.py), 10x10 grid",
             "traffic": "TrafficManagementEnv (oracle/traffic_port.py; measured 1.5x FASTER than the real reference "
                        "in the build container, 2.9k vs 1.9k steps/s, so a conservative baseline), default config"
             }[env_name]
@@ -330,6 +347,8 @@ def make_env(pkg, env_name, n, dev, seed, base):
         return pkg.BatchedCryptoTradingEnv(n, None, "discrete", device=dev, seed=seed, env_id_base=base)
     if env_name == "climate":
         return pkg.BatchedSmartClimateEnv(n, device=dev, seed=seed, env_id_base=base)
+    if env_name == "builder":
+        return pkg.BatchedWorldBuilderEnv(n, device=dev, seed=seed, env_id_base=base)
     return pkg.BatchedTrafficManagementEnv(n, device=dev, seed=seed, env_id_base=base)
 
 
@@ -346,6 +365,8 @@ def kernel_description(lib, env_name, n):
                 "(1 env warp + 3 window warps)")
     if env_name == "climate":
         return "beng::climate_kernel<T=256,IS_RESET=false>: one thread per env, 256-env tile per CTA"
+    if env_name == "builder":
+        return "beng::builder_kernel<T=128,IS_RESET=false>: one thread per env, 128-env grid tile per CTA"
     return "beng::traffic_kernel<NI=9,T=64,IS_RESET=false>: one thread per env, 64-env tile per CTA"
 
 
@@ -472,6 +493,13 @@ def run_b200_arm(args):
     if args.env == "snake":
         stats = all_reduce_episode_stats(env.stats)
         summary = summarize(stats)
+    elif args.env == "builder":
+        st = env.stats.clone()
+        if world > 1:
+            dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        v = st.tolist()
+        summary = {"episodes": v[0], "episode_return_mean": v[1] / max(v[0], 1), "episode_len_mean": v[2] / max(v[0], 1),
+                   "wins": v[3]}
     else:
         st = env.stats.clone()
         if world > 1:
@@ -494,6 +522,7 @@ def run_b200_arm(args):
     api = {"snake": "BatchedSnakeEnv.step_host -> beng_snake_step_host",
            "crypto": "BatchedCryptoTradingEnv.step_host -> beng_crypto_step_host",
            "climate": "BatchedSmartClimateEnv.step_host -> beng_climate_step_host",
+           "builder": "BatchedWorldBuilderEnv.step_host -> beng_builder_step_host",
            "traffic": "BatchedTrafficManagementEnv.step_host -> beng_traffic_step_host"}[args.env]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -542,7 +571,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--env", choices=sorted(WORKLOADS), default="snake",
                     help="snake = the BASELINE.json headline (configs[1]); crypto = configs[2]; traffic = configs[3]; "
-                         "climate = SURVEY.md 8(f) rank 3 (no BASELINE config)")
+                         "climate, builder = SURVEY.md 8(f) rank 3 (no BASELINE config)")
     ap.add_argument("--envs-per-gpu", type=int, default=None)
     ap.add_argument("--action-pool", type=int, default=256, help="distinct pre-generated action steps kept in HBM")
     ap.add_argument("--e2e-steps", type=int, default=20)
