@@ -81,8 +81,13 @@ __global__ void __launch_bounds__(T) builder_kernel(const BArgs a) {
         int rew = 0, term = 0;
         bool invalid = false;
 
+        // Rows start on 4-byte boundaries when G*G is a multiple of 4 (G even, e.g. the default 10): the three loops
+        // over the row (clear, count empty cells, find the k-th empty cell) then run word-wise, 4 cells at a time.
+        const bool wordwise = (cells & 3) == 0;
+        uint32_t *row32 = reinterpret_cast<uint32_t *>(row);
         auto reset_env = [&]() {  // world_builder_env.py:99-123 + game_logic.py:33-57
-            for (int i = 0; i < cells; ++i) row[i] = 0;
+            if (wordwise) { for (int i = 0; i < (cells >> 2); ++i) row32[i] = 0u; }
+            else { for (int i = 0; i < cells; ++i) row[i] = 0; }
             food = 25; wood = 20; stone = 10; pop = 3; cap = 10;
             counts = 0; steps = 0; win_steps = 0; reached = 0; flags = 0; ep_ret = 0;
         };
@@ -105,14 +110,32 @@ __global__ void __launch_bounds__(T) builder_kernel(const BArgs a) {
                             : (action == QUARRY) ? wood >= 5 : (wood >= 10 && stone >= 5);  // _can_afford_building
                     int n_empty = 0;
                     if (ok) {
-                        for (int i = 0; i < cells; ++i) n_empty += (row[i] == 0);
+                        if (wordwise) {  // __vcmpeq4: 0xFF in every byte lane that equals zero
+                            for (int i = 0; i < (cells >> 2); ++i) n_empty += __popc(__vcmpeq4(row32[i], 0u)) >> 3;
+                        } else {
+                            for (int i = 0; i < cells; ++i) n_empty += (row[i] == 0);
+                        }
                         ok = n_empty > 0;  // "No empty space", :133-134
                     }
                     if (ok) {
                         int idx = rng.randint(0, n_empty - 1);  // np.random.randint(n_empty), :137
                         int pos = 0;
-                        for (int i = 0; i < cells; ++i) {
-                            if (row[i] == 0 && idx-- == 0) { pos = i; break; }
+                        if (wordwise) {
+                            for (int i = 0; i < (cells >> 2); ++i) {
+                                const uint32_t m = __vcmpeq4(row32[i], 0u);
+                                const int c = __popc(m) >> 3;
+                                if (idx < c) {  // the idx-th empty byte lane of this word (row-major = little-endian lanes)
+                                    uint32_t lanes = m & 0x01010101u;  // one bit per empty lane
+                                    for (int k = 0; k < idx; ++k) lanes &= lanes - 1;  // drop the first idx empty lanes
+                                    pos = i * 4 + ((__ffs(lanes) - 1) >> 3);
+                                    break;
+                                }
+                                idx -= c;
+                            }
+                        } else {
+                            for (int i = 0; i < cells; ++i) {
+                                if (row[i] == 0 && idx-- == 0) { pos = i; break; }
+                            }
                         }
                         if (action == FARM) wood -= 5;
                         else if (action == LUMBERYARD) stone -= 3;
