@@ -144,12 +144,13 @@ def load():
     """Load libbeng.so (once).  Raises RuntimeError when it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        lib_path = os.environ.get("BENG_LIB_PATH", LIB_PATH)  # A/B a different build of the same ABI (profiling only)
+        if not os.path.exists(lib_path):
             raise RuntimeError(
                 f"{LIB_PATH} is missing: the CUDA engine has not been built and there is no CPU fallback. "
                 "Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or custom_gymnasium_environments_b200._build.build_library()).")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(lib_path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = res
