@@ -361,13 +361,14 @@ def kernel_description(lib, env_name, n):
         return (f"beng::snake_kernel<T={t_.value},STAGES={s_.value},IS_RESET=false,OWNROW=true>, "
                 f"{c_.value} persistent CTAs/SM")
     if env_name == "crypto":
-        return ("beng::crypto_kernel<T=32,IS_RESET=false>: 128-thread warp-specialised CTA per 32-env tile "
-                "(1 env warp + 3 window warps)")
+        return ("beng::crypto2_kernel<IS_RESET=false>: 256-thread CTA, two phases per tile (per-env float64 dynamics, "
+                "then the 261-feature window/indicator tile cooperatively)")
     if env_name == "climate":
-        return "beng::climate_kernel<T=256,IS_RESET=false>: one thread per env, 256-env tile per CTA"
+        return "beng::climate_kernel<T=128,IS_RESET=false>: one thread per env, 128-env tile per CTA, 8 CTAs per SM"
     if env_name == "builder":
         return "beng::builder_kernel<T=128,IS_RESET=false>: one thread per env, 128-env grid tile per CTA"
-    return "beng::traffic_kernel<NI=9,T=64,IS_RESET=false>: one thread per env, 64-env tile per CTA"
+    return ("beng::traffic_wpi_kernel<NI=9,IS_RESET=false>: 320-thread CTA per 32 envs, one warp per intersection + "
+            "one env warp")
 
 
 def run_b200_arm(args):

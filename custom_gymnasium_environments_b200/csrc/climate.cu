@@ -41,7 +41,7 @@ __device__ __forceinline__ double outside_temp(double tod, EnvStream &rng) {
 }
 
 template <int T, bool IS_RESET>
-__global__ void __launch_bounds__(T) climate_kernel(const KArgs a) {
+__global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
     __shared__ __align__(128) float tile[T * KOBS];
     const int tid = threadIdx.x;
     const long long n = a.n;
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(T) climate_kernel(const KArgs a) {
     if (tid == 0) bulk_wait_read<0>();
 }
 
-constexpr int CLIMATE_T = 256;
+constexpr int CLIMATE_T = 128;
 
 template <bool IS_RESET>
 int launch(const KArgs &a, cudaStream_t stream) {

@@ -283,7 +283,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 // (L2-coherent) after barrier A.
 template <int T, bool IS_RESET>
 __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
-    constexpr int NT = 4 * T, NW = 3 * T;  // threads, window threads
     constexpr int OLD = HIST - 1;          // candles that exist before this step
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);                                    // [T][261]
@@ -1113,7 +1112,6 @@ int launch_split(const CArgs &a, cudaStream_t stream) {
     return (int)e;
 }
 
-constexpr int CRYPTO_T = 32;  // envs per CTA (128 threads): 33.4 KB obs tile + 12.5 KB close staging, 4 CTAs per SM
 
 template <int T>
 constexpr size_t crypto_smem_bytes() {

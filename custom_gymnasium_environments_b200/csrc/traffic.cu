@@ -16,9 +16,10 @@
 // observation are float64 expressions of those integers in the reference's operation order (np.var = NumPy's
 // pairwise sums), cast to float32 -- bit-exact against the reference.
 //
-// One thread per env over [field][env] arrays (coalesced); the T x obs_dim float observation tile is composed in
-// shared memory and drained with one bulk asynchronous copy (cp.async.bulk, UBLKCP).  HBM-bound on paper
-// (~1.2 KB per env-step) but at 65,536 envs one step is only ~80 MB, so launch latency matters as much.
+// One warp per intersection, one lane per env, over [field][env] arrays (coalesced); the 32 x obs_dim float
+// observation tile is composed in shared memory and drained with one bulk asynchronous copy (cp.async.bulk,
+// UBLKCP).  HBM-bound on paper (~1.2 KB per env-step); what limits it in practice is the per-env serial chain
+// loads -> spawn -> queues -> reward, see the kernel comment.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -44,30 +45,69 @@ struct TArgs {
     int ni, first_call;
 };
 
-// NumPy's pairwise summation (np.var in _calculate_reward), n <= 128
-template <int CAP>
-__device__ __forceinline__ double np_sum(const double (&a)[CAP], int n) {
+// NumPy's pairwise summation (np.var in _calculate_reward, n <= 128) over f(0..n-1), without materialising the array
+template <typename F>
+__device__ __forceinline__ double np_sum_fn(F f, int n) {
     if (n < 8) {
         double r = 0.0;
-        for (int i = 0; i < n; ++i) r += a[i];
+        for (int i = 0; i < n; ++i) r += f(i);
         return r;
     }
     double r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    for (int j = 0; j < 8; ++j) r[j] = f(j);
     int i = 8;
     for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+        for (int j = 0; j < 8; ++j) r[j] += f(i + j);
     }
     double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < n; ++i) res += a[i];
+    for (; i < n; ++i) res += f(i);
     return res;
 }
 
+// (float)((double)a / (double)b) for non-negative integers.  When both are exactly representable in binary32 the
+// correctly rounded binary32 quotient is the same number (rounding a binary64 quotient of two binary32 values to
+// binary32 is innocuous: 53 >= 2*24+2), so the common case is one IEEE float division instead of an FP64 one.
+__device__ __forceinline__ float ratio_f32(long long a, long long b) {
+    if (a < (1 << 24) && b < (1 << 24)) return __fdiv_rn((float)(int)a, (float)(int)b);
+    return (float)((double)a / (double)b);
+}
+
+// The env warp's view of the env stream: the first SPEC_BLOCKS Philox blocks at/after the step's starting counter
+// are computed BEFORE barrier 1 (while the intersection warps wait for their loads) and parked in shared memory, so
+// the spawn logic between barriers 1 and 2 -- which every intersection warp waits for -- is table look-ups.  Draws
+// beyond the table (many lights turning green in one step) fall back to computing their block.
+constexpr int SPEC_BLOCKS = 3;
+
+__device__ __noinline__ uint32_t philox_draw(uint32_t idx, uint64_t env, uint64_t seed) {
+    const Philox4 p = philox4x32_10(idx >> 2, (uint32_t)env, (uint32_t)(env >> 32), BENG_STREAM_ENV, (uint32_t)seed,
+                                    (uint32_t)(seed >> 32));
+    const uint32_t l = idx & 3u;
+    return l == 0 ? p.v[0] : l == 1 ? p.v[1] : l == 2 ? p.v[2] : p.v[3];
+}
+
+struct CachedStream {
+    uint32_t ctr;
+    uint32_t first;          // index of the first cached draw (a multiple of 4)
+    const uint32_t *cache;   // [SPEC_BLOCKS * 4][32] in shared memory, already offset by the lane
+    uint64_t env, seed;
+    __device__ __forceinline__ uint32_t u32() {
+        const uint32_t idx = ctr++, rel = idx - first;
+        if (rel < SPEC_BLOCKS * 4) return cache[rel * 32];
+        return philox_draw(idx, env, seed);
+    }
+    __device__ __forceinline__ int randint(int a, int b) { return a + (int)__umulhi(u32(), (uint32_t)(b - a + 1)); }
+    __device__ __forceinline__ double random53() {
+        const uint32_t a = u32() >> 5, b = u32() >> 6;
+        return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+    }
+};
+
 // generate_vehicle_route (utils.py:174-193) + get_direction_between_intersections (:230-248) reduced to what the
 // dynamics use: the first hop's direction and whether the walk ends on its start.
-__device__ __forceinline__ void spawn_route(const TArgs &a, EnvStream &rng, int &start, int &dir, int &loopback) {
+template <typename Stream>
+__device__ __forceinline__ void spawn_route(const TArgs &a, Stream &rng, int &start, int &dir, int &loopback) {
     const int rows = a.p.grid_rows, cols = a.p.grid_cols;
     start = rng.randint(0, a.ni - 1);
     const int route_length = rng.randint(2, a.ni < 5 ? a.ni : 5);
@@ -90,293 +130,331 @@ __device__ __forceinline__ void spawn_route(const TArgs &a, EnvStream &rng, int 
     loopback = (row * cols + col) == start;
 }
 
-template <int NI_T, int T, bool IS_RESET>
-__global__ void __launch_bounds__(T) traffic_kernel(const TArgs a) {
-    constexpr int CAP = NI_T ? NI_T : MAXNI;
+// ---------------------------------------------------------------------------------------------------------------
+// Step / reset kernel: one WARP per intersection, one lane per env.
+//
+// (The first version of this kernel ran one thread per env: ~2,500 dependent instructions per thread, 198 registers,
+// ~8 resident warps per SM and 31 % of its stall samples on instruction-cache misses)  A CTA
+// of NI+1 warps owns 32 envs: warp i < NI steps intersection i of those envs (its [field][env] rows are read with
+// fully coalesced requests), warp NI is the env warp (spawn, reward, termination, counters).  The two roles run
+// different code between the same CTA-wide barriers; what crosses intersections goes through shared memory:
+//   barrier 1: which lights need a randint draw (one ballot word per intersection) -> every light knows the index
+//              of its own draw in the env's Philox stream (counter-based, so any thread can compute any draw)
+//   barrier 2: the vehicle spawned this step (env warp, after the light draws in stream order)
+//   barrier 3: per-intersection passed / waiting / queue totals -> reward (env warp), global metrics (warp 0)
+//   barrier 4: observation tile complete -> one bulk asynchronous copy per CTA
+// Every intersection warp waits for the env warp between barriers 1-2 and 3-4, so the env warp's code there is kept
+// short: its Philox blocks are computed ahead of barrier 1 (CachedStream), the global metrics are warp 0's.
+constexpr int WPI_E = 32;  // envs per CTA
+
+template <int NI_T, bool IS_RESET>
+__global__ void __maxnreg__(NI_T ? 48 : 72) traffic_wpi_kernel(const TArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tile = reinterpret_cast<float *>(smem_raw);
     const int NI = NI_T ? NI_T : a.ni;
     const int OD = NI * 14 + 4;
-    const int tid = threadIdx.x;
+    float *tile = reinterpret_cast<float *>(smem_raw);                       // [32][OD]
+    int32_t *s_part = reinterpret_cast<int32_t *>(tile + WPI_E * OD);         // [4][NI][32]
+    int32_t *s_spawn = s_part + 4 * NI * WPI_E;                               // [32]
+    uint32_t *s_phx = reinterpret_cast<uint32_t *>(s_spawn + WPI_E);          // [SPEC_BLOCKS*4][32]
+    uint32_t *s_need = s_phx + SPEC_BLOCKS * 4 * WPI_E;                        // [NI]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n = a.n;
-    const long long first = (long long)blockIdx.x * T;
-    const long long env = first + tid;
+    const long long first = (long long)blockIdx.x * WPI_E;
+    const long long env = first + lane;
     const bool active = env < n;
-    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
-    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
+    float *row = tile + lane * OD;
+    // the two roles run different code between the same CTA-wide barriers (arrival is counted per warp)
+    auto cta_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"r"((NI + 1) * 32) : "memory"); };
+    pdl_launch_dependents();
+    pdl_wait();
 
-    bool ended = false;
-    double st_ret = 0.0, st_len = 0.0;
+    // env header, read by every warp of the CTA (same 128-byte lines: L1 hits after the first)
+    uint32_t m0 = 0, ctr = 0;
+    bool selected = true;
     if (active) {
-        float *row = tile + tid * OD;
-        uint32_t m0 = a.st.misc[env];
-        int timestep = m0 & 0xFFFF;
-        uint32_t flags = m0 >> 16;
-        int listed = (int)a.st.misc[n + env];
-        uint32_t ctr = a.st.misc[2 * n + env];
-        double total_reward = a.st.total_reward[env];
-        bool do_reset = false, selected = true;
-        double rew = 0.0;
-        int term = 0;
-        if constexpr (IS_RESET) {
-            if (a.mask) selected = a.mask[env] != 0;
-            do_reset = selected;
-            if (selected && a.first_call) ctr = 0;
-        } else {
-            do_reset = a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & TFLAG_NEEDS_RESET);
-        }
-        EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
+        m0 = a.st.misc[env];
+        ctr = a.st.misc[2 * n + env];
+        if (IS_RESET && a.mask) selected = a.mask[env] != 0;
+    }
+    int timestep = m0 & 0xFFFF;
+    uint32_t flags = m0 >> 16;
+    const bool do_reset =
+        IS_RESET ? selected : (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & TFLAG_NEEDS_RESET));
+    if (IS_RESET && selected && a.first_call) ctr = 0;
+    const bool stepping = !IS_RESET && !do_reset && active;
+    if (stepping) timestep = min(timestep + 1, 65535);                                  // :170
+    const bool term = stepping && timestep >= a.p.max_timesteps;                        // :196, reported as terminated
+    const bool ended = term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED;
+    const bool same_step = ended && a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP;
 
-        // Bring the whole env state into registers with independent, fully coalesced loads issued back to back (one
-        // round of memory latency instead of one per intersection); everything below works on these copies.
-        uint32_t L[CAP], QM[CAP * 4];
-        int P[CAP], Wt[CAP], QW[CAP * 4];
-        long long ACT[CAP];
+    if (w < NI) {
+        // ================= intersection warp: intersection i of 32 envs =================
+        const int i = w;
+        // ---- phase A: loads; _apply_actions (:205-220) + TrafficLight.update (utils.py:79-97)
+        uint32_t l0 = 0, qm0[4] = {0, 0, 0, 0};
+        int passed = 0, wait = 0, qw0[4] = {0, 0, 0, 0};
+        long long act = 0;
+        if (active) {
+            l0 = a.st.light[(long long)i * n + env];
+            passed = a.st.passed[(long long)i * n + env];
+            wait = a.st.waiting[(long long)i * n + env];
 #pragma unroll
-        for (int i = 0; i < CAP; ++i) {
-            if (i < NI) {
-                L[i] = a.st.light[(long long)i * n + env];
-                P[i] = a.st.passed[(long long)i * n + env];
-                Wt[i] = a.st.waiting[(long long)i * n + env];
-                if constexpr (!IS_RESET) ACT[i] = a.actions[env * NI + i];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    QM[i * 4 + d] = a.st.qmeta[(long long)(i * 4 + d) * n + env];
-                    QW[i * 4 + d] = a.st.qwait[(long long)(i * 4 + d) * n + env];
-                }
+            for (int d = 0; d < 4; ++d) {
+                qm0[d] = a.st.qmeta[(long long)(i * 4 + d) * n + env];
+                qw0[d] = a.st.qwait[(long long)(i * 4 + d) * n + env];
             }
+            if constexpr (!IS_RESET) act = a.actions[env * NI + i];
         }
-
-        int sp_i = -1, sp_d = 0, sp_lb = 0;  // vehicle spawned this step: start intersection, direction, loop-back
-        if (!IS_RESET && !do_reset) {
-            timestep = min(timestep + 1, 65535);  // :170
-            // _apply_actions (:205-220) then TrafficLight.update (utils.py:79-97), lights in id order
-#pragma unroll
-            for (int i = 0; i < CAP; ++i) {
-                if (i >= NI) break;
-                const uint32_t l = L[i];
-                int phase = l & 0xFF, timer = (int)(l >> 8);
-                const long long act = ACT[i];
-                if (act == 1 && phase != NS_GREEN) { phase = NS_GREEN; timer = 5; }       // set_phase: MIN_PHASE_DURATION
+        int phase = l0 & 0xFF, timer = (int)(l0 >> 8);
+        int spawn = -1;
+        if constexpr (!IS_RESET) {
+            bool need = false;
+            if (stepping) {
+                if (act == 1 && phase != NS_GREEN) { phase = NS_GREEN; timer = 5; }    // set_phase: MIN_PHASE_DURATION
                 else if (act == 2 && phase != EW_GREEN) { phase = EW_GREEN; timer = 5; }
                 timer -= 1;
-                if (timer <= 0) {                                                        // _advance_phase
+                if (timer <= 0) {                                                      // _advance_phase
                     phase = (phase + 1) & 3;
-                    timer = (phase & 1) ? 3 : rng.randint(5, 30);                        // YELLOW_DURATION | randint
-                }
-                const uint32_t nl = (uint32_t)phase | ((uint32_t)timer << 8);
-                if (nl != l) a.st.light[(long long)i * n + env] = (uint16_t)nl;
-                L[i] = nl;
-            }
-            // _spawn_vehicles (:222-249)
-            if (listed < a.p.max_vehicles) {
-                if (rng.random53() < a.p.spawn_rate) {
-                    spawn_route(a, rng, sp_i, sp_d, sp_lb);
-                    listed += 1;
+                    if (phase & 1) timer = 3;                                          // YELLOW_DURATION
+                    else need = true;                                                  // randint(5, 30), after barrier 1
                 }
             }
+            const unsigned nb = __ballot_sync(0xFFFFFFFFu, need);
+            if (lane == 0) s_need[i] = nb;
+            cta_barrier();  // barrier 1
+            if (need) {  // lights draw in id order: this one's draw follows those of the lower ids
+                uint32_t before = 0;
+                for (int j = 0; j < i; ++j) before += (s_need[j] >> lane) & 1u;
+                EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr + before);
+                timer = rng.randint(5, 30);
+            }
+            cta_barrier();  // barrier 2
+            spawn = s_spawn[lane];
         }
 
-        // _process_intersections (:271-281, utils.py:141-163), _remove_completed_vehicles (:283-285), and the
-        // per-intersection parts of reward (:287-311) and observation (:313-363), one pass over the intersections.
-        long long tot_passed = 0, tot_wait = 0, tot_queue = 0;
-        double qt[CAP];
+        // ---- phase B: _process_intersections (:271-281, utils.py:141-163), _remove_completed_vehicles (:283-285)
+        // and the per-intersection features of the observation (:313-363)
+        if (active) {
+            const int sp_d = (spawn >> 8) & 0xFF, sp_lb = (spawn >> 16) & 0xFF;
+            const bool sp_here = spawn >= 0 && (spawn & 0xFF) == i;
+            const int passed0 = passed, wait0 = wait;  // as loaded
+            if (do_reset) { phase = NS_GREEN; timer = 0; passed = 0; wait = 0; }
+            int qsum = 0, left = 0;
+            const bool wipe = do_reset || same_step;  // fresh TrafficLight (NS_GREEN, timer 0), empty queues, zero counters
 #pragma unroll
-        for (int i = 0; i < CAP; ++i) {
-            if (i < NI) {
-                int phase = NS_GREEN, passed = 0, wait = 0;
-                if (do_reset) {  // reset (:141-166): fresh TrafficLight (NS_GREEN, timer 0), empty queues, zero counters
-                    a.st.light[(long long)i * n + env] = (uint16_t)NS_GREEN;
-                    a.st.passed[(long long)i * n + env] = 0;
-                    a.st.waiting[(long long)i * n + env] = 0;
-                } else {
-                    phase = L[i] & 0xFF;
-                    passed = P[i];
-                    wait = Wt[i];
-                }
-                const int passed0 = passed, wait0 = wait;
-                int qsum = 0;
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const long long qi = (long long)(i * 4 + d) * n + env;
-                    int cnt = 0, lb = 0, qw = 0;
-                    uint32_t qm0 = 0;
-                    int qw0 = 0;
-                    if (do_reset) {
-                        a.st.qmeta[qi] = 0;
-                        a.st.qwait[qi] = 0;
-                    } else {
-                        qm0 = QM[i * 4 + d];
-                        qw0 = QW[i * 4 + d];
-                        cnt = qm0 & 0xFF;
-                        lb = qm0 >> 8;
-                        qw = qw0;
-                        if (!IS_RESET) {
-                            if (i == sp_i && d == sp_d) { cnt += 1; lb += sp_lb; }  // add_vehicle_to_queue, waiting_time 0
-                            if (cnt) {
-                                const bool green = (phase == NS_GREEN && (d == NORTH || d == SOUTH)) ||
-                                                   (phase == EW_GREEN && (d == EAST || d == WEST));  // can_pass
-                                if (green) {  // the whole queue proceeds; loop-back vehicles leave self.vehicles
-                                    passed += cnt;
-                                    listed -= lb;
-                                    cnt = 0; lb = 0; qw = 0;
-                                } else {      // every queued vehicle waits one more step
-                                    qw += cnt;
-                                    wait += cnt;
-                                }
+            for (int d = 0; d < 4; ++d) {
+                const long long qi = (long long)(i * 4 + d) * n + env;
+                int cnt = 0, lb = 0, qw = 0;
+                if (!do_reset) {
+                    cnt = qm0[d] & 0xFF;
+                    lb = qm0[d] >> 8;
+                    qw = qw0[d];
+                    if (stepping) {
+                        if (sp_here && d == sp_d) { cnt += 1; lb += sp_lb; }  // add_vehicle_to_queue, waiting_time 0
+                        if (cnt) {
+                            const bool green = (phase == NS_GREEN && (d == NORTH || d == SOUTH)) ||
+                                               (phase == EW_GREEN && (d == EAST || d == WEST));  // can_pass
+                            if (green) {  // the whole queue proceeds; loop-back vehicles leave self.vehicles
+                                passed += cnt;
+                                left += lb;
+                                cnt = 0; lb = 0; qw = 0;
+                            } else {      // every queued vehicle waits one more step
+                                qw += cnt;
+                                wait += cnt;
                             }
-                            const uint32_t qm = (uint32_t)cnt | ((uint32_t)lb << 8);
-                            if (qm != qm0) a.st.qmeta[qi] = (uint16_t)qm;
-                            if (qw != qw0) a.st.qwait[qi] = qw;
                         }
                     }
-                    qsum += cnt;
-                    row[NI * 4 + i * 4 + d] = (float)min(cnt, 20);                          // MAX_QUEUE_LENGTH
-                    const double avg = cnt ? (double)qw / (double)cnt : 0.0;
-                    row[NI * 8 + i * 4 + d] = (float)(avg < 100.0 ? avg : 100.0);
                 }
-                if (!do_reset && !IS_RESET) {
-                    if (passed != passed0) a.st.passed[(long long)i * n + env] = passed;
-                    if (wait != wait0) a.st.waiting[(long long)i * n + env] = wait;
+                qsum += cnt;
+                if (wipe) {
+                    if (qm0[d]) a.st.qmeta[qi] = 0;
+                    if (qw0[d]) a.st.qwait[qi] = 0;
+                    cnt = 0; qw = 0;
+                } else if (stepping) {
+                    const uint32_t qm = (uint32_t)cnt | ((uint32_t)lb << 8);
+                    if (qm != qm0[d]) a.st.qmeta[qi] = (uint16_t)qm;
+                    if (qw != qw0[d]) a.st.qwait[qi] = qw;
                 }
-#pragma unroll
-                for (int ph = 0; ph < 4; ++ph) row[i * 4 + ph] = (phase == ph) ? 1.0f : 0.0f;
-                row[NI * 12 + i * 2] = (float)passed;
-                row[NI * 12 + i * 2 + 1] = (float)min(wait, 1000);
-                tot_passed += passed;
-                tot_wait += wait;
-                tot_queue += qsum;
-                qt[i] = (double)qsum;
+                row[NI * 4 + i * 4 + d] = (float)min(cnt, 20);                            // MAX_QUEUE_LENGTH
+                row[NI * 8 + i * 4 + d] = cnt ? fminf(ratio_f32(qw, cnt), 100.0f) : 0.0f;   // mean waiting time, <= 100
             }
-        }
-
-        if (do_reset) {
-            timestep = 0;
-            total_reward = 0.0;
-            listed = 0;
-            flags = 0;
-        } else if (!IS_RESET) {
-            // _calculate_reward (:287-311): CUMULATIVE counters, float64, the reference's order of additions
-            rew = 0.0;
-            rew += (double)tot_passed * 1.0;
-            rew += (double)tot_wait * -0.1;
-            rew += (double)tot_queue * -0.05;
-            if (NI > 1) {
-                const double mean = np_sum(qt, NI) / (double)NI;
-                double sq[CAP];
+            s_part[(0 * NI + i) * WPI_E + lane] = passed;
+            s_part[(1 * NI + i) * WPI_E + lane] = wait;
+            s_part[(2 * NI + i) * WPI_E + lane] = qsum;
+            s_part[(3 * NI + i) * WPI_E + lane] = left;
+            uint32_t nl = (uint32_t)phase | ((uint32_t)timer << 8);
+            if (wipe) { nl = NS_GREEN; passed = 0; wait = 0; phase = NS_GREEN; }
+            if (nl != l0) a.st.light[(long long)i * n + env] = (uint16_t)nl;
+            if (passed != passed0) a.st.passed[(long long)i * n + env] = passed;
+            if (wait != wait0) a.st.waiting[(long long)i * n + env] = wait;
 #pragma unroll
-                for (int i = 0; i < CAP; ++i) {
-                    if (i < NI) { const double dq = qt[i] - mean; sq[i] = dq * dq; }
-                }
-                const double var = np_sum(sq, NI) / (double)NI;  // np.var: population variance
-                rew += 0.5 / (1 + var);
-            }
-            total_reward += rew;
-            term = timestep >= a.p.max_timesteps;  // :196, reported as terminated
+            for (int ph = 0; ph < 4; ++ph) row[i * 4 + ph] = (phase == ph) ? 1.0f : 0.0f;
+            row[NI * 12 + i * 2] = (float)passed;
+            row[NI * 12 + i * 2 + 1] = (float)min(wait, 1000);
         }
-
-        // global metrics (utils.py:251-267, environment.py:352-361)
-        const double avg_wait = (double)tot_wait / (double)(tot_passed > 1 ? tot_passed : 1);
-        const double avg_queue = (double)tot_queue / (double)NI;
-        row[NI * 14 + 0] = (float)listed;
-        row[NI * 14 + 1] = (float)(avg_wait < 100.0 ? avg_wait : 100.0);
-        row[NI * 14 + 2] = (float)(avg_queue < 50.0 ? avg_queue : 50.0);
-        row[NI * 14 + 3] = (float)((double)tot_passed / (double)NI);
-
-        if (!IS_RESET && term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
-            ended = true;
-            st_ret = total_reward;
-            st_len = (double)timestep;
-            if (a.io.ep_return) a.io.ep_return[env] = total_reward;
-            if (a.io.ep_length) a.io.ep_length[env] = timestep;
-            if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) {
-                // reset() draws nothing and its observation is a constant: rewrite state + row in place
-                for (int i = 0; i < NI; ++i) {
-                    a.st.light[(long long)i * n + env] = (uint16_t)NS_GREEN;
-                    a.st.passed[(long long)i * n + env] = 0;
-                    a.st.waiting[(long long)i * n + env] = 0;
-                    for (int d = 0; d < 4; ++d) {
-                        a.st.qmeta[(long long)(i * 4 + d) * n + env] = 0;
-                        a.st.qwait[(long long)(i * 4 + d) * n + env] = 0;
-                    }
+        cta_barrier();  // barrier 3
+        if (i == 0 && active) {
+            // global metrics (utils.py:251-267, environment.py:352-361), off the env warp's critical path
+            int tot_passed = 0, tot_wait = 0, tot_queue = 0;
+            if (!same_step) {
+                for (int j = 0; j < NI; ++j) {
+                    tot_passed += s_part[(0 * NI + j) * WPI_E + lane];
+                    tot_wait += s_part[(1 * NI + j) * WPI_E + lane];
+                    tot_queue += s_part[(2 * NI + j) * WPI_E + lane];
                 }
-                for (int k = 0; k < OD; ++k) row[k] = 0.0f;
-                for (int i = 0; i < NI; ++i) row[i * 4] = 1.0f;  // every light NS_GREEN
+            }
+            row[NI * 14 + 1] = fminf(ratio_f32(tot_wait, tot_passed > 1 ? tot_passed : 1), 100.0f);
+            row[NI * 14 + 2] = fminf(ratio_f32(tot_queue, NI), 50.0f);
+            row[NI * 14 + 3] = ratio_f32(tot_passed, NI);
+        }
+    } else {
+        // ================= env warp: spawn, reward, termination, global metrics, counters =================
+        int listed = 0;
+        double total_reward = 0.0;
+        if (active) {
+            listed = (int)a.st.misc[n + env];
+            total_reward = a.st.total_reward[env];
+        }
+        if constexpr (!IS_RESET) {
+            const uint64_t env_id = a.p.env_id_base + (uint64_t)env;
+            const uint32_t blk0 = ctr >> 2;
+            if (stepping) {
+#pragma unroll
+                for (int b = 0; b < SPEC_BLOCKS; ++b) {
+                    const Philox4 ph = philox4x32_10(blk0 + b, (uint32_t)env_id, (uint32_t)(env_id >> 32),
+                                                     BENG_STREAM_ENV, (uint32_t)a.p.seed, (uint32_t)(a.p.seed >> 32));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s_phx[(b * 4 + k) * WPI_E + lane] = ph.v[k];
+                }
+            }
+            cta_barrier();  // barrier 1
+            uint32_t draws = 0;
+            for (int j = 0; j < NI; ++j) draws += (s_need[j] >> lane) & 1u;
+            ctr += draws;
+            int spawn = -1;
+            // _spawn_vehicles (:222-249)
+            if (stepping && listed < a.p.max_vehicles) {
+                CachedStream rng{ctr, blk0 << 2, s_phx + lane, env_id, a.p.seed};
+                if (rng.random53() < a.p.spawn_rate) {
+                    int sp_i, sp_d, sp_lb;
+                    spawn_route(a, rng, sp_i, sp_d, sp_lb);
+                    listed += 1;
+                    spawn = sp_i | (sp_d << 8) | (sp_lb << 16);
+                }
+                ctr = rng.ctr;
+            }
+            s_spawn[lane] = spawn;
+            cta_barrier();  // barrier 2
+        }
+        cta_barrier();  // barrier 3
+
+        // ---- phase C: _calculate_reward (:287-311), termination, global metrics
+        double st_ret = 0.0, st_len = 0.0;
+        if (active) {
+            long long tot_passed = 0, tot_wait = 0, tot_queue = 0;
+            for (int i = 0; i < NI; ++i) {
+                tot_passed += s_part[(0 * NI + i) * WPI_E + lane];
+                tot_wait += s_part[(1 * NI + i) * WPI_E + lane];
+                tot_queue += s_part[(2 * NI + i) * WPI_E + lane];
+                listed -= s_part[(3 * NI + i) * WPI_E + lane];
+            }
+            double rew = 0.0;
+            if (do_reset) {
                 timestep = 0;
                 total_reward = 0.0;
                 listed = 0;
                 flags = 0;
-            } else {
-                flags |= TFLAG_NEEDS_RESET;
+            } else if (!IS_RESET) {
+                // CUMULATIVE counters, float64, the reference's order of additions
+                rew += (double)tot_passed * 1.0;
+                rew += (double)tot_wait * -0.1;
+                rew += (double)tot_queue * -0.05;
+                if (NI > 1) {
+                    const int32_t *q = s_part + 2 * NI * WPI_E + lane;  // queue total of intersection i at q[i * 32]
+                    const double mean = np_sum_fn([&](int i) { return (double)q[i * WPI_E]; }, NI) / (double)NI;
+                    const double var =
+                        np_sum_fn([&](int i) { const double dq = (double)q[i * WPI_E] - mean; return dq * dq; }, NI) /
+                        (double)NI;  // np.var: population variance
+                    rew += 0.5 / (1 + var);
+                }
+                total_reward += rew;
+            }
+            if (ended) {
+                st_ret = total_reward;
+                st_len = (double)timestep;
+                if (a.io.ep_return) a.io.ep_return[env] = total_reward;
+                if (a.io.ep_length) a.io.ep_length[env] = timestep;
+                if (same_step) {  // reset() draws nothing and its observation is a constant
+                    timestep = 0;
+                    total_reward = 0.0;
+                    listed = 0;
+                    flags = 0;
+                } else {
+                    flags |= TFLAG_NEEDS_RESET;
+                }
+            }
+            row[NI * 14 + 0] = (float)listed;  // len(self.vehicles); the other three global metrics: warp 0
+
+            a.st.misc[env] = (uint32_t)timestep | (flags << 16);
+            a.st.misc[n + env] = (uint32_t)listed;
+            a.st.misc[2 * n + env] = ctr;
+            a.st.total_reward[env] = total_reward;
+            if constexpr (!IS_RESET) {
+                a.io.reward[env] = (float)rew;
+                a.io.terminated[env] = (uint8_t)term;
+                if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term);  // raw class: 0, :197
+                if (a.io.reward64) a.io.reward64[env] = rew;
             }
         }
-
-        a.st.misc[env] = (uint32_t)timestep | (flags << 16);
-        a.st.misc[n + env] = (uint32_t)listed;
-        a.st.misc[2 * n + env] = rng.ctr;
-        a.st.total_reward[env] = total_reward;
         if constexpr (!IS_RESET) {
-            a.io.reward[env] = (float)rew;
-            a.io.terminated[env] = (uint8_t)term;
-            if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term);  // raw class: 0, :197
-            if (a.io.reward64) a.io.reward64[env] = rew;
+            if (a.io.stats) {
+                const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+                if (done_mask) {
+                    double r = st_ret, l = st_len;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+                        l += __shfl_xor_sync(0xFFFFFFFFu, l, o);
+                    }
+                    if (lane == 0) {
+                        atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
+                        atomicAdd(&a.io.stats[1], r);
+                        atomicAdd(&a.io.stats[2], l);
+                    }
+                }
+            }
         }
     }
 
     fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-        const long long n_here = min((long long)T, n - first);
+    cta_barrier();  // barrier 4: the observation tile is complete
+    if (threadIdx.x == 0) {
+        const long long n_here = min((long long)WPI_E, n - first);
         const uint32_t bytes = (uint32_t)(n_here * OD * sizeof(float));
         const uint32_t bulk = bytes & ~15u;
         if (bulk) bulk_store_s2g(a.io.obs + first * OD, tile, bulk);
         bulk_commit();
         for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[first * OD + i] = tile[i];  // ragged last tile
+        bulk_wait_read<0>();
     }
-    if constexpr (!IS_RESET) {
-        if (a.io.stats) {
-            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
-            if (done_mask) {
-                double r = st_ret, l = st_len;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
-                    l += __shfl_xor_sync(0xFFFFFFFFu, l, o);
-                }
-                if ((tid & 31) == 0) {
-                    atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
-                    atomicAdd(&a.io.stats[1], r);
-                    atomicAdd(&a.io.stats[2], l);
-                }
-            }
-        }
-    }
-    if (tid == 0) bulk_wait_read<0>();
 }
 
-constexpr int TRAFFIC_T = 64;  // envs (= threads) per CTA; 64 x 520 B = 33 KB observation tile
-
-template <int NI_T, int T, bool IS_RESET>
-int launch_t(const TArgs &a, cudaStream_t stream) {
-    const size_t smem = (size_t)T * (a.ni * 14 + 4) * sizeof(float);
-    const unsigned grid = (unsigned)((a.n + T - 1) / T);
-    auto kern = traffic_kernel<NI_T, T, IS_RESET>;
+template <int NI_T, bool IS_RESET>
+int launch_wpi(const TArgs &a, cudaStream_t stream) {
+    const int od = a.ni * 14 + 4;
+    const size_t smem = (size_t)WPI_E * od * sizeof(float) + (size_t)(4 * a.ni * WPI_E + WPI_E + SPEC_BLOCKS * 4 * WPI_E + a.ni) * sizeof(int32_t);
+    const unsigned grid = (unsigned)((a.n + WPI_E - 1) / WPI_E);
+    auto kern = traffic_wpi_kernel<NI_T, IS_RESET>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    e = launch_pdl(kern, dim3(grid), dim3(T), smem, stream, a);
+    e = launch_pdl(kern, dim3(grid), dim3((a.ni + 1) * 32), smem, stream, a);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return (int)e;
 }
 
 template <bool IS_RESET>
 int launch(const TArgs &a, cudaStream_t stream) {
-    static int tile = -1;  // BENG_TRAFFIC_TILE=32|64 (read once; profiling sweeps)
-    if (tile < 0) {
-        const char *e = getenv("BENG_TRAFFIC_TILE");
-        tile = e ? atoi(e) : TRAFFIC_T;
-    }
-    if (a.ni == 9) return tile == 32 ? launch_t<9, 32, IS_RESET>(a, stream) : launch_t<9, 64, IS_RESET>(a, stream);
-    return launch_t<0, 64, IS_RESET>(a, stream);
+    return a.ni == 9 ? launch_wpi<9, IS_RESET>(a, stream) : launch_wpi<0, IS_RESET>(a, stream);
 }
 
 int check(const beng_traffic_params *p, const beng_traffic_state *st, const beng_traffic_io *io, int64_t n) {

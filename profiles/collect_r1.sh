@@ -6,7 +6,7 @@ out=gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q > $out/pytest_gpu_r1.log 2>&1; echo "pytest rc=$?"; tail -2 $out/pytest_gpu_r1.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_r1.log 2>&1; echo "smoke rc=$?"; tail -1 $out/smoke_r1.log
 for env in snake crypto traffic climate builder; do
-  kern=${env}_kernel; [ $env = crypto ] && kern=crypto2_kernel
+  kern=${env}_kernel; [ $env = crypto ] && kern=crypto2_kernel; [ $env = traffic ] && kern=traffic_wpi_kernel
   B="python bench.py --env $env --steps 120 --warmup 40 --no-cpu-baseline --e2e-steps 1 --no-l2-flush"
   $B > $out/plain_$env.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:$kern -s 100 -c 1 -o $out/prof_${env}_r1_final $B > $out/ncu_full_$env.log 2>&1
   skip=200; [ $env = climate ] && skip=60   # the climate run builds its tapes with a handful of torch launches

@@ -10,6 +10,11 @@ if name == "crypto":
     n = 1 << 18; env = pkg.BatchedCryptoTradingEnv(n, None, "discrete", device=dev); acts = torch.randint(0, 5, (64, n), device=dev)
 elif name == "snake":
     n = 1 << 20; env = pkg.BatchedSnakeEnv(n, device=dev); acts = torch.randint(0, 4, (64, n), device=dev)
+elif name == "climate":
+    n = 1 << 20; env = pkg.BatchedSmartClimateEnv(n, device=dev)
+    acts = [{"ac_temp": torch.rand(n, device=dev) * 16 + 16, "lights": torch.randint(0, 2, (n, 4), device=dev).to(torch.int8)} for _ in range(64)]
+elif name == "builder":
+    n = 1 << 20; env = pkg.BatchedWorldBuilderEnv(n, device=dev); acts = torch.randint(0, 5, (64, n), device=dev)
 else:
     n = 1 << 16; env = pkg.BatchedTrafficManagementEnv(n, device=dev); acts = torch.randint(0, 3, (64, n, 9), device=dev)
 env.reset()
