@@ -366,7 +366,7 @@ def kernel_description(lib, env_name, n):
     if env_name == "climate":
         return "beng::climate_kernel<T=128,IS_RESET=false>: one thread per env, 128-env tile per CTA, 8 CTAs per SM"
     if env_name == "builder":
-        return "beng::builder_kernel<T=128,IS_RESET=false>: one thread per env, 128-env grid tile per CTA"
+        return "beng::builder_kernel<T=64,IS_RESET=false>: one thread per env, 64-env grid tile per CTA"
     return ("beng::traffic_wpi_kernel<NI=9,IS_RESET=false>: 192-thread CTA per 32 envs, five intersection warps (2 each) + "
             "one env warp")
 

@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
     bool ended = false;
     double st_ret = 0.0, st_len = 0.0;
     if (env < n) {
+        // the action is requested together with the state, not after the state has arrived and been inspected
+        float act_ac = 0.0f;
+        uint32_t lw = 0;
+        if constexpr (!IS_RESET) {
+            act_ac = a.ac_temp[env];
+            lw = *reinterpret_cast<const uint32_t *>(a.lights + 4 * env);  // four int8 flags
+        }
         double room = a.st.f64[env], outside = a.st.f64[n + env], ac = a.st.f64[2 * n + env];
         double total = a.st.f64[3 * n + env], energy = a.st.f64[4 * n + env];
         const uint32_t w0 = (uint32_t)a.st.i32[env];
@@ -88,8 +95,7 @@ __global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
             if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & KFLAG_NEEDS_RESET)) {
                 init_state();
             } else {
-                ac = kclip((double)a.ac_temp[env], 16.0, 32.0);  // env.py:85
-                const uint32_t lw = *reinterpret_cast<const uint32_t *>(a.lights + 4 * env);  // four int8 flags
+                ac = kclip((double)act_ac, 16.0, 32.0);  // env.py:85
                 int lights_on = 0;
                 lights = 0;
 #pragma unroll

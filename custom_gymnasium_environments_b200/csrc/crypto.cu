@@ -566,6 +566,16 @@ __global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
     {
         const long long env = first + tid;
         if (env < n) {
+            // requested together with the state (they are only used on the ordinary step path, but waiting for the flags
+            // to arrive before asking for them would put a second memory round trip at the head of the chain)
+            double price_pre = 0.0;
+            long long act_pre = 0;
+            float2 actf_pre = make_float2(0.0f, 0.0f);
+            if constexpr (!IS_RESET) {
+                price_pre = a.st.close[(long long)a.p.window_head * n + env];
+                if (a.p.action_type == 1) actf_pre = reinterpret_cast<const float2 *>(a.actions)[env];
+                else act_pre = reinterpret_cast<const long long *>(a.actions)[env];
+            }
             double cash = a.st.scal[env], holdings = a.st.scal[n + env];
             Market m;
             m.trend = a.st.scal[2 * n + env];
@@ -615,16 +625,16 @@ __global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
                     value = cash + holdings * price_out;
                 } else {
                     // _execute_action, :400-447
-                    const double price = a.st.close[(long long)a.p.window_head * n + env];
+                    const double price = price_pre;
                     const double initial_value = cash + holdings * price;
                     if (a.p.action_type == 1) {
-                        const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
+                        const float2 act = actf_pre;
                         const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
                         const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
                         if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
                         else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
                     } else {
-                        const long long act = reinterpret_cast<const long long *>(a.actions)[env];
+                        const long long act = act_pre;
                         if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
                         else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
                         else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
