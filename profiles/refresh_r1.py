@@ -1,6 +1,10 @@
 #!/usr/bin/env python
-"""Copy what profiles/collect_r1b.sh left in gpurun_out/ into profiles/ (tracked) and regenerate the derived files:
-ncu summaries, launch shares of the refreshed envs, and the <env>_step_traffic.json files bench.py reads."""
+"""Copy what profiles/collect_r1.sh (all envs) or collect_r1b.sh (traffic, climate) left in gpurun_out/ into profiles/
+(tracked) and regenerate the derived files: ncu summaries, launch shares of the refreshed envs, and the
+<env>_step_traffic.json files bench.py reads.
+
+    python profiles/refresh_r1.py [env ...]        # default: traffic climate
+"""
 import collections
 import csv
 import json
@@ -9,14 +13,17 @@ import re
 import shutil
 import subprocess
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-ENVS = {"traffic": 65536, "climate": 1 << 20}
+SIZES = {"snake": 1 << 20, "crypto": 1 << 18, "traffic": 1 << 16, "climate": 1 << 20, "builder": 1 << 20}
+ENVS = {e: SIZES[e] for e in (sys.argv[1:] or ["traffic", "climate"])}
 
-for name in ("bench_r1_traffic_n1.json", "bench_r1_traffic_n1_1m_envs.json", "bench_r1_climate_n1.json",
-             "pytest_gpu_r1.log", "smoke_r1.log"):
-    shutil.copy(os.path.join(OUT, name), os.path.join(PROF, name))
+for name in [f"bench_r1_{e}_n1.json" for e in ENVS] + ["bench_r1_traffic_n1_1m_envs.json", "bench_r1_snake_reference.json",
+                                                         "pytest_gpu_r1.log", "smoke_r1.log"]:
+    if os.path.exists(os.path.join(OUT, name)) and os.path.getmtime(os.path.join(OUT, name)) > time.time() - 6 * 3600:
+        shutil.copy(os.path.join(OUT, name), os.path.join(PROF, name))
 for env in ENVS:
     shutil.copy(os.path.join(OUT, f"launches_{env}_r1.csv"), os.path.join(PROF, f"{env}_r1_launches.csv"))
     with open(os.path.join(PROF, f"{env}_step_r1_ncu_summary.txt"), "w") as f:
