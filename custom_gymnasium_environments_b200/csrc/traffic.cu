@@ -164,6 +164,8 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
     const long long first = (long long)blockIdx.x * WPI_E;
     const long long env = first + lane;
     const bool active = env < n;
+    // element offsets fit 32 bits (check() refuses n * ni * 4 >= 2^32): one IMAD.WIDE per address instead of 64-bit chains
+    const uint32_t un = (uint32_t)n, e32 = (uint32_t)env;
     float *row = tile + lane * OD;
     // the two roles run different code between the same CTA-wide barriers (arrival is counted per warp)
     auto cta_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"r"((NW + 1) * 32) : "memory"); };
@@ -174,8 +176,8 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
     uint32_t m0 = 0, ctr = 0;
     bool selected = true;
     if (active) {
-        m0 = a.st.misc[env];
-        ctr = a.st.misc[2 * n + env];
+        m0 = a.st.misc[e32];
+        ctr = a.st.misc[2u * un + e32];
         if (IS_RESET && a.mask) selected = a.mask[env] != 0;
     }
     int timestep = m0 & 0xFFFF;
@@ -203,15 +205,15 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
 #pragma unroll
             for (int d = 0; d < 4; ++d) { qm0[k][d] = 0; qw0[k][d] = 0; }
             if (active && i < NI) {
-                l0[k] = a.st.light[(long long)i * n + env];
-                passed[k] = a.st.passed[(long long)i * n + env];
-                wait[k] = a.st.waiting[(long long)i * n + env];
+                l0[k] = a.st.light[(uint32_t)i * un + e32];
+                passed[k] = a.st.passed[(uint32_t)i * un + e32];
+                wait[k] = a.st.waiting[(uint32_t)i * un + e32];
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
-                    qm0[k][d] = a.st.qmeta[(long long)(i * 4 + d) * n + env];
-                    qw0[k][d] = a.st.qwait[(long long)(i * 4 + d) * n + env];
+                    qm0[k][d] = a.st.qmeta[(uint32_t)(i * 4 + d) * un + e32];
+                    qw0[k][d] = a.st.qwait[(uint32_t)(i * 4 + d) * un + e32];
                 }
-                if constexpr (!IS_RESET) act[k] = a.actions[env * NI + i];
+                if constexpr (!IS_RESET) act[k] = a.actions[e32 * (uint32_t)NI + (uint32_t)i];
             }
         }
         int spawn = -1;
@@ -269,7 +271,7 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
                 int qsum = 0, left = 0;
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
-                    const long long qi = (long long)(i * 4 + d) * n + env;
+                    const uint32_t qi = (uint32_t)(i * 4 + d) * un + e32;
                     int cnt = 0, lb = 0, qw = 0;
                     if (!do_reset) {
                         cnt = qm0[k][d] & 0xFF;
@@ -310,9 +312,9 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
                 s_part[(3 * NI + i) * WPI_E + lane] = left;
                 uint32_t nl = (uint32_t)ph | ((uint32_t)tm << 8);
                 if (wipe) { nl = NS_GREEN; pas = 0; wt = 0; ph = NS_GREEN; }
-                if (nl != l0[k]) a.st.light[(long long)i * n + env] = (uint16_t)nl;
-                if (pas != passed[k]) a.st.passed[(long long)i * n + env] = pas;
-                if (wt != wait[k]) a.st.waiting[(long long)i * n + env] = wt;
+                if (nl != l0[k]) a.st.light[(uint32_t)i * un + e32] = (uint16_t)nl;
+                if (pas != passed[k]) a.st.passed[(uint32_t)i * un + e32] = pas;
+                if (wt != wait[k]) a.st.waiting[(uint32_t)i * un + e32] = wt;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) row[i * 4 + q] = (ph == q) ? 1.0f : 0.0f;
                 row[NI * 12 + i * 2] = (float)pas;
@@ -339,7 +341,7 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
         int listed = 0;
         double total_reward = 0.0;
         if (active) {
-            listed = (int)a.st.misc[n + env];
+            listed = (int)a.st.misc[un + e32];
             total_reward = a.st.total_reward[env];
         }
         if constexpr (!IS_RESET) {
@@ -378,8 +380,8 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
         if (active) {
             if (do_reset || same_step) { timestep = 0; flags = 0; }
             else if (ended) flags |= TFLAG_NEEDS_RESET;
-            a.st.misc[env] = (uint32_t)timestep | (flags << 16);
-            a.st.misc[2 * n + env] = ctr;
+            a.st.misc[e32] = (uint32_t)timestep | (flags << 16);
+            a.st.misc[2u * un + e32] = ctr;
             if constexpr (!IS_RESET) {
                 a.io.terminated[env] = (uint8_t)term;
                 if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term);  // raw class: 0, :197
@@ -427,7 +429,7 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
                 }
             }
             row[NI * 14 + 0] = (float)listed;  // len(self.vehicles); the other three global metrics: warp 0
-            a.st.misc[n + env] = (uint32_t)listed;
+            a.st.misc[un + e32] = (uint32_t)listed;
             a.st.total_reward[env] = total_reward;
             if constexpr (!IS_RESET) {
                 a.io.reward[env] = (float)rew;
@@ -503,6 +505,7 @@ int check(const beng_traffic_params *p, const beng_traffic_state *st, const beng
     if (ni > MAXNI || p->max_vehicles < 0 || p->max_vehicles > 255) return BENG_ERR_UNSUPPORTED;
     if (p->max_timesteps < 1 || p->max_timesteps > 65535) return BENG_ERR_UNSUPPORTED;
     if (cells < 2) return BENG_ERR_UNSUPPORTED;  // a 1x1 grid has no neighbours to route to
+    if ((unsigned long long)n * (unsigned long long)ni * 4ull >= (1ull << 32)) return BENG_ERR_UNSUPPORTED;  // 32-bit offsets
     return 0;
 }
 
