@@ -285,7 +285,9 @@ int beng_traffic_reset(const beng_traffic_params *p, const beng_traffic_state *s
 /* TrafficManagementEnv.step (environment.py:168-203): _apply_actions, every TrafficLight.update, _spawn_vehicles
  * (+ generate_vehicle_route), _process_intersections, _remove_completed_vehicles, _calculate_reward,
  * _get_observation and auto-reset, for all envs, in ONE kernel launch.  actions_dev: int64 [n][ni], values
- * 0 keep / 1 NS_GREEN / 2 EW_GREEN (anything else keeps, like the reference). */
+ * 0 keep / 1 NS_GREEN / 2 EW_GREEN (anything else keeps, like the reference).  The kernels address the [field][env]
+ * arrays with 32-bit element offsets: n_envs * ni * 4 must be below 2^32 (119 M envs on the default 9-intersection grid),
+ * otherwise BENG_ERR_UNSUPPORTED. */
 int beng_traffic_step(const beng_traffic_params *p, const beng_traffic_state *st, const int64_t *actions_dev,
                       const beng_traffic_io *io, int64_t n_envs, void *stream);
 
