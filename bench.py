@@ -8,8 +8,11 @@ A "step" is ONE launch of the fused step kernel over the whole batch, inputs res
 envs x steps x ranks / max-over-ranks device time (CUDA events).  `e2e` is the same metric through the
 host-buffer C-ABI call (`beng_<env>_step_host`: pinned host actions in, numpy obs/reward/terminated out, copies
 inside the timed region).  `roofline` uses SURVEY.md 8(d)'s algorithmic bytes per env-step against the measured HBM
-copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times the pure-Python port of the reference's per-env step
-loop (oracle/*_port.py; the reference itself cannot travel to the GPU box) on the host cores, rank 0 at N=1 only.
+copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` times the UNMODIFIED reference class in its own per-env Python
+step loop (oracle/ref_loader.py: /root/reference here, the byte-for-byte copies staged under oracle/_ref by
+`python -m oracle.make_ref` on the GPU box; `kind: "reference"`, the oracle port only if neither exists) on the host
+cores, rank 0 at N=1 only.  The default `--env snake` run appends device-timed crypto and traffic blocks (BASELINE
+configs[2], [3]) as `secondary`.
 
 Prints exactly one JSON line on stdout (rank 0).
 """
@@ -72,80 +75,104 @@ WORKLOADS = {
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's per-env Python step loop (port), one env per process
+# CPU arm: the reference's own per-env Python step loop, one env per process
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker_loop(args):
-    """Step one ported env with random actions and reset-on-done for `n_steps` steps (the loop shape of
-    crypto_trading_env/test_crypto_trading.py:410-416).  Returns (steps, seconds)."""
-    env_name, worker, n_steps = args
+def reference_kind() -> str:
+    """"reference" when the unmodified reference classes can be imported (/root/reference in the build container,
+    oracle/_ref on the GPU box -- staged by `python -m oracle.make_ref`), else "port" (oracle/*_port.py)."""
+    from oracle import ref_loader
+
+    return "reference" if ref_loader.reference_available() else "port"
+
+
+def _make_cpu_env(env_name, worker, kind):
+    """-> (env, sample_action).  kind "reference": the UNMODIFIED reference class behind the stub gymnasium/pygame
+    (oracle/ref_loader.py), seeded through the module-level RNGs it really uses; kind "port": oracle/*_port.py."""
     import random
 
+    import numpy as np
+
     rng = random.Random(1234 + worker)
-    if env_name == "snake":
-        from oracle.snake_port import SnakePort
+    randrange, uniform = rng.randrange, rng.uniform
+    samplers = {
+        "snake": lambda: randrange(4),
+        "crypto": lambda: randrange(5),
+        "builder": lambda: randrange(5),
+        # MultiDiscrete([3]*9) sample, like env.action_space.sample() in traffic_management_env/test_env.py:266-278
+        "traffic": lambda: np.array([randrange(3) for _ in range(9)]),
+        # Dict action sample: ac_temp Box(16, 32, (1,)), lights MultiBinary(4)
+        "climate": lambda: {"ac_temp": np.array([uniform(16.0, 32.0)], dtype=np.float32),
+                            "lights": np.array([randrange(2) for _ in range(4)], dtype=np.int8)},
+    }
+    if kind == "reference":
+        import logging
 
-        env, n_act = SnakePort(20, rng=rng), 4
-    elif env_name == "crypto":
-        import numpy as np
+        from oracle import ref_loader
 
-        from oracle.crypto_port import CryptoPort
-
-        np.random.seed(1234 + worker)
-        env, n_act = CryptoPort(action_type="discrete"), 5
-    elif env_name == "builder":
-        import numpy as np
-
-        from oracle.builder_port import BuilderPort
-
-        np.random.seed(1234 + worker)
-        env, n_act = BuilderPort(), 5
-    elif env_name == "climate":
-        import numpy as np
-
-        from oracle.climate_port import ClimatePort
-
-        env, n_act = ClimatePort(seed=1234 + worker), 2
+        random.seed(4321 + worker)      # snake / crypto / traffic draw from the process-global `random` ...
+        np.random.seed(4321 + worker)   # ... crypto and world_builder also from `np.random`
+        if env_name == "snake":
+            env = ref_loader.load_snake().SnakeEnvClassic()
+        elif env_name == "crypto":
+            env = ref_loader.load_crypto().CryptoTradingEnv(action_type="discrete")
+        elif env_name == "traffic":
+            env = ref_loader.load_traffic()[0].TrafficManagementEnv()
+        elif env_name == "climate":
+            env = ref_loader.load_climate().SmartClimateEnv(log_level=logging.ERROR)
+        else:
+            env = ref_loader.load_builder()[0].WorldBuilderEnv()
     else:
-        import numpy as np
+        if env_name == "snake":
+            from oracle.snake_port import SnakePort
 
-        from oracle.traffic_port import TrafficPort
+            env = SnakePort(20, rng=rng)
+        elif env_name == "crypto":
+            from oracle.crypto_port import CryptoPort
 
-        env, n_act = TrafficPort(rng=rng), 3
+            np.random.seed(1234 + worker)
+            env = CryptoPort(action_type="discrete")
+        elif env_name == "builder":
+            from oracle.builder_port import BuilderPort
+
+            np.random.seed(1234 + worker)
+            env = BuilderPort()
+        elif env_name == "climate":
+            from oracle.climate_port import ClimatePort
+
+            env = ClimatePort(seed=1234 + worker)
+        else:
+            from oracle.traffic_port import TrafficPort
+
+            env = TrafficPort(rng=rng)
+    return env, samplers[env_name]
+
+
+def _cpu_worker_loop(args):
+    """Step one env with random actions and reset-on-done for `n_steps` steps -- the loop shape of the reference's own
+    harness, crypto_trading_env/test_crypto_trading.py:410-416.  Returns (steps, seconds)."""
+    env_name, worker, n_steps, kind = args
+    env, sample = _make_cpu_env(env_name, worker, kind)
     env.reset()
-    randrange = rng.randrange
+    step, reset = env.step, env.reset
     t0 = time.perf_counter()
-    if env_name == "climate":
-        uniform = rng.uniform
-        for _ in range(n_steps):  # Dict action sample: ac_temp Box(16, 32, (1,)), lights MultiBinary(4)
-            act = {"ac_temp": np.array([uniform(16.0, 32.0)], dtype=np.float32),
-                   "lights": np.array([randrange(2) for _ in range(4)], dtype=np.int8)}
-            _, _, term, trunc, _ = env.step(act)
-            if term or trunc:
-                env.reset()
-    elif env_name == "traffic":
-        for _ in range(n_steps):  # MultiDiscrete([3]*9) sample, like env.action_space.sample() in traffic test_env.py:266-278
-            _, _, term, trunc, _ = env.step(np.array([randrange(3) for _ in range(9)]))
-            if term or trunc:
-                env.reset()
-    else:
-        for _ in range(n_steps):
-            _, _, term, trunc, _ = env.step(randrange(n_act))
-            if term or trunc:
-                env.reset()
+    for _ in range(n_steps):
+        _, _, term, trunc, _ = step(sample())
+        if term or trunc:
+            reset()
     return n_steps, time.perf_counter() - t0
 
 
-def cpu_rate_single(env_name: str, seconds: float) -> float:
+def cpu_rate_single(env_name: str, seconds: float, kind: str) -> float:
     probe = WORKLOADS[env_name].cpu_single_steps
-    n, dt = _cpu_worker_loop((env_name, 0, probe))
+    n, dt = _cpu_worker_loop((env_name, 0, probe, kind))
     rate = n / dt
-    n, dt = _cpu_worker_loop((env_name, 0, max(probe, int(rate * seconds))))
+    n, dt = _cpu_worker_loop((env_name, 0, max(probe, int(rate * seconds)), kind))
     return n / dt
 
 
-def cpu_rate_parallel(pool, env_name: str, procs: int, steps_per_proc: int):
+def cpu_rate_parallel(pool, env_name: str, procs: int, steps_per_proc: int, kind: str):
     t0 = time.perf_counter()
-    res = pool.map(_cpu_worker_loop, [(env_name, w, steps_per_proc) for w in range(procs)])
+    res = pool.map(_cpu_worker_loop, [(env_name, w, steps_per_proc, kind) for w in range(procs)])
     wall = time.perf_counter() - t0
     return sum(r[0] for r in res) / wall, wall
 
@@ -195,16 +222,16 @@ def c_oracle_rate(env_name: str, seconds: float = 1.5) -> float:
     return n * k / (time.perf_counter() - t0)
 
 
-def port_description(env_name, cores, per_proc):
-    what = {"snake": "SnakeEnvClassic (oracle/snake_port.py), G=20",
-            "crypto": "CryptoTradingEnv (oracle/crypto_port.py), discrete actions",
-            "climate": "SmartClimateEnv (oracle/climate_port.py), default config",
-            "builder": "WorldBuilderEnv (oracle/builder_port.py), 10x10 grid",
-            "traffic": "TrafficManagementEnv (oracle/traffic_port.py; measured 1.5x FASTER than the real reference "
-                       "in the build container, 2.9k vs 1.9k steps/s, so a conservative baseline), default config"
-            }[env_name]
-    return (f"pure-Python port of {what}: 1 env per process x {cores} processes x {per_proc} random-action "
-            "steps with reset-on-done")
+def cpu_arm_description(env_name, kind, cores, per_proc):
+    ref = {"snake": "snake_env_classic/snake_env.py SnakeEnvClassic, G=20",
+           "crypto": "crypto_trading_env/crypto_trading_env.py CryptoTradingEnv, discrete actions",
+           "traffic": "traffic_management_env/environment.py TrafficManagementEnv, default config",
+           "climate": "smartclimate/env.py SmartClimateEnv, default config",
+           "builder": "world_builder_env WorldBuilderEnv, 10x10 grid"}[env_name]
+    what = (f"the UNMODIFIED reference class ({ref}) behind stub gymnasium/pygame" if kind == "reference"
+            else f"pure-Python port (oracle/{env_name}_port.py) of {ref}")
+    return (f"{what}: 1 env per process x {cores} processes x {per_proc} random-action steps with reset-on-done "
+            f"(os.cpu_count() = {os.cpu_count()})")
 
 
 def run_reference_arm(args):
@@ -213,28 +240,32 @@ def run_reference_arm(args):
         return  # rank 0 alone runs the CPU arm
     w = WORKLOADS[args.env]
     cores = os.cpu_count() or 1
-    single = cpu_rate_single(args.env, 1.0)
+    kind = reference_kind()
+    single = cpu_rate_single(args.env, 1.0, kind)
     budget_s = 60.0
     per_step = int(min(50000, max(20, single * budget_s / max(1, args.steps + args.warmup))))
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_rate_parallel(pool, args.env, cores, per_step)
+            cpu_rate_parallel(pool, args.env, cores, per_step, kind)
         t0 = time.perf_counter()
         total = 0
         for _ in range(args.steps):
-            res = pool.map(_cpu_worker_loop, [(args.env, k, per_step) for k in range(cores)])
+            res = pool.map(_cpu_worker_loop, [(args.env, k, per_step, kind) for k in range(cores)])
             total += sum(r[0] for r in res)
         wall = time.perf_counter() - t0
     value = total / wall
+    baseline = {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": cpu_arm_description(args.env, kind, cores, per_step) + " per bench step",
+                "single_core_value": single}
+    if kind == "reference":  # the port's rate beside it, for continuity with round 1
+        baseline["port_single_core_value"] = cpu_rate_single(args.env, 1.0, "port")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
         "config": workload_config(args, per_gpu=args.envs_per_gpu),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": port_description(args.env, cores, per_step) + " per bench step",
-                         "single_core_value": single},
+        "cpu_baseline": baseline,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -302,8 +333,8 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def workload_config(args, per_gpu):
-    w = WORKLOADS[args.env]
+def workload_config(args, per_gpu, env_name=None):
+    w = WORKLOADS[env_name or args.env]
     mb = per_gpu * w.bytes / 1e6
     if per_gpu * w.bytes < 2 * 126e6 and not getattr(args, "no_l2_flush", False):
         l2 = (f"L2 flushed between timed steps: one step moves only {mb:.0f} MB (< 126 MB L2), so every step is timed "
@@ -331,13 +362,15 @@ def load_peak():
 
 
 def load_traffic(env_name, n_envs):
-    """Per-launch DRAM bytes of the step kernel from the committed ncu capture (profiles/), scaled to this batch."""
+    """Per-launch DRAM bytes of the step kernel from the COMMITTED ncu capture (profiles/<env>_step_traffic.json,
+    builder-run), scaled to this batch.  Not measured in this run: -> (bytes or None, where it comes from)."""
+    path = os.path.join("profiles", f"{env_name}_step_traffic.json")
     try:
-        with open(os.path.join(ROOT, "profiles", f"{env_name}_step_traffic.json")) as f:
+        with open(os.path.join(ROOT, path)) as f:
             d = json.load(f)
-        return d["dram_bytes_per_env_step"] * n_envs
+        return d["dram_bytes_per_env_step"] * n_envs, f"{path} (ncu --set full capture, builder-run; not measured in this run)"
     except Exception:
-        return None
+        return None, None
 
 
 def make_env(pkg, env_name, n, dev, seed, base):
@@ -361,8 +394,8 @@ def kernel_description(lib, env_name, n):
         return (f"beng::snake_kernel<T={t_.value},STAGES={s_.value},IS_RESET=false,OWNROW=true>, "
                 f"{c_.value} persistent CTAs/SM")
     if env_name == "crypto":
-        return ("beng::crypto2_kernel<IS_RESET=false>: 256-thread CTA, two phases per tile (per-env float64 dynamics, "
-                "then the 261-feature window/indicator tile cooperatively)")
+        return ("beng::crypto3_kernel<IS_RESET=false>: persistent 256-thread CTAs over 32-env units; per-env float64 "
+                "dynamics, then the window is streamed once (indicators accumulated on the way) into the 261-feature tile")
     if env_name == "climate":
         return "beng::climate_kernel<T=128,IS_RESET=false>: one thread per env, 128-env tile per CTA, 8 CTAs per SM"
     if env_name == "builder":
@@ -371,36 +404,63 @@ def kernel_description(lib, env_name, n):
             "one env warp")
 
 
-def run_b200_arm(args):
-    import torch
-    import torch.distributed as dist
+API_NAMES = {"snake": "BatchedSnakeEnv.step_host -> beng_snake_step_host",
+             "crypto": "BatchedCryptoTradingEnv.step_host -> beng_crypto_step_host",
+             "climate": "BatchedSmartClimateEnv.step_host -> beng_climate_step_host",
+             "builder": "BatchedWorldBuilderEnv.step_host -> beng_builder_step_host",
+             "traffic": "BatchedTrafficManagementEnv.step_host -> beng_traffic_step_host"}
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("BENG_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's banner goes to stdout and would precede the JSON line
 
-    import custom_gymnasium_environments_b200 as pkg
-    from custom_gymnasium_environments_b200.dist import all_reduce_episode_stats, init_process_group, summarize
+def pin_to_gpu_numa_node(local_rank):
+    """Bind this process to the CPUs NVML names as local to its GPU, so that the pinned host buffers it allocates next
+    (first touch) and the copy-issuing thread sit on the GPU's NUMA node.  -> (bound?, previous affinity)."""
+    prev = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    try:
+        import pynvml
 
-    rank, local_rank, world = init_process_group()
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    lib = pkg._lib.load()
-    w = WORKLOADS[args.env]
-    n = args.envs_per_gpu
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        return True, prev
+    except Exception:
+        return False, prev
+
+
+def pcie_ceiling(torch, dev, nbytes):
+    """Measured pinned-memory D2H and H2D `cudaMemcpyAsync` bandwidth (GB/s) for one buffer of `nbytes`."""
+    nbytes = int(max(1 << 20, min(nbytes, 1 << 30)))
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    out = {}
+    for name, (dst, src) in {"d2h": (h, d), "h2d": (d, h)}.items():
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        best = 0.0
+        for _ in range(3):
+            t0 = time.perf_counter()
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            best = max(best, nbytes / (time.perf_counter() - t0) / 1e9)
+        out[name] = best
+    return out
+
+
+def bench_env(ctx, env_name, n, steps, warmup, e2e_steps):
+    """Time one env's step kernel (device-resident) and its host-buffer C-ABI call (end to end) on every rank.
+    Returns the measurement block on rank 0 (None elsewhere).  All ranks must call this in the same order."""
+    torch, dist, pkg, lib, args = ctx["torch"], ctx["dist"], ctx["pkg"], ctx["lib"], ctx["args"]
+    rank, local_rank, world, dev = ctx["rank"], ctx["local_rank"], ctx["world"], ctx["dev"]
+    from custom_gymnasium_environments_b200.dist import all_reduce_episode_stats, summarize
+
+    w = WORKLOADS[env_name]
     seed = 0
     base = rank * n  # contiguous global env-id slice per rank (weak scaling)
-
-    env = make_env(pkg, args.env, n, dev, seed, base)
+    env = make_env(pkg, env_name, n, dev, seed, base)
     env.reset()
     stream = torch.cuda.current_stream(dev)
 
     # action tapes, resident in HBM before the timed region (pool of distinct steps, cycled)
-    pool = max(64, min(args.steps + args.warmup, args.action_pool))
-    if args.env == "climate":  # Dict action: ac_temp float32 (n,), lights int8 (n, 4), torch-generated tapes
+    pool = max(64, min(steps + warmup, args.action_pool))
+    if env_name == "climate":  # Dict action: ac_temp float32 (n,), lights int8 (n, 4), torch-generated tapes
         gen = torch.Generator(device=dev).manual_seed(1234 + rank)
         ac_t = torch.rand((pool, n), device=dev, generator=gen) * 16.0 + 16.0
         li_t = torch.randint(0, 2, (pool, n, 4), device=dev, generator=gen).to(torch.int8)
@@ -425,7 +485,7 @@ def run_b200_arm(args):
     # step, which would stay L2-resident: there every step is timed on its own events with a 256 MB fill in between
     # (the warm, back-to-back figure is reported separately as `value_l2_warm`).
     flush = n * w.bytes < 2 * 126e6 and not args.no_l2_flush
-    for t in range(args.warmup):
+    for t in range(warmup):
         env.step(tapes[t % pool])
     torch.cuda.synchronize(dev)
     barrier()
@@ -435,8 +495,8 @@ def run_b200_arm(args):
     torch.cuda.synchronize(dev)
     sampler.start()
     ev0.record(stream)
-    for t in range(args.steps):
-        env.step(tapes[(args.warmup + t) % pool])
+    for t in range(steps):
+        env.step(tapes[(warmup + t) % pool])
     ev1.record(stream)
     torch.cuda.synchronize(dev)
     launches = lib.beng_launch_count() - launches0
@@ -444,12 +504,12 @@ def run_b200_arm(args):
     ms = ms_warm
     if flush:
         scratch = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         launches0 = lib.beng_launch_count()
-        for t in range(args.steps):
+        for t in range(steps):
             scratch.fill_(t & 0xFF)  # evicts the previous step's lines from L2 (not timed)
             pairs[t][0].record(stream)
-            env.step(tapes[(args.warmup + t) % pool])
+            env.step(tapes[(warmup + t) % pool])
             pairs[t][1].record(stream)
         torch.cuda.synchronize(dev)
         launches = lib.beng_launch_count() - launches0
@@ -461,13 +521,13 @@ def run_b200_arm(args):
     if world > 1:
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms_max = float(ms_t.item())
-    value = n * world * args.steps / (ms_max * 1e-3)
-    value_warm = n * world * args.steps / (ms_warm * 1e-3)
+    value = n * world * steps / (ms_max * 1e-3)
+    value_warm = n * world * steps / (ms_warm * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI call -------------------------------------------
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    e2e_steps = max(1, min(steps, e2e_steps))
     host_tapes = [to_host(tapes[t % pool]) for t in range(min(e2e_steps + 2, 8))]
-    h2d = n * 8 if args.env == "climate" else n * 8 * w.n_cols
+    h2d = n * 8 if env_name == "climate" else n * 8 * w.n_cols
     d2h_full = n * (w.obs_bytes + w.result_bytes)
     d2h_lite = n * w.result_bytes
 
@@ -485,22 +545,22 @@ def run_b200_arm(args):
         dt_t = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-        return n * world * e2e_steps / float(dt_t.item())
+        return n * world * e2e_steps / float(dt_t.item()), float(dt_t.item()) / e2e_steps
 
-    e2e_full = time_e2e(True)
-    e2e_lite = time_e2e(False)
+    e2e_full, e2e_s_per_step = time_e2e(True)
+    e2e_lite, _ = time_e2e(False)
+    # the link ceiling for THIS rank's big D2H copy, measured with plain pinned cudaMemcpyAsync right after (all ranks
+    # at once at N > 1, like the e2e loop itself), so that e2e can be read as a fraction of what the platform gives
+    barrier()
+    link = pcie_ceiling(torch, dev, n * w.obs_bytes)
+    link_t = torch.tensor([link["d2h"], link["h2d"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(link_t, op=dist.ReduceOp.MIN)
+    link_d2h, link_h2d = (float(v) for v in link_t.tolist())
 
     # ---- episode statistics: the only collective, outside the step loop ---------------------------
-    if args.env == "snake":
-        stats = all_reduce_episode_stats(env.stats)
-        summary = summarize(stats)
-    elif args.env == "builder":
-        st = env.stats.clone()
-        if world > 1:
-            dist.all_reduce(st, op=dist.ReduceOp.SUM)
-        v = st.tolist()
-        summary = {"episodes": v[0], "episode_return_mean": v[1] / max(v[0], 1), "episode_len_mean": v[2] / max(v[0], 1),
-                   "wins": v[3]}
+    if env_name == "snake":
+        summary = summarize(all_reduce_episode_stats(env.stats))
     else:
         st = env.stats.clone()
         if world > 1:
@@ -508,35 +568,38 @@ def run_b200_arm(args):
         v = st.tolist()
         summary = {"episodes": int(v[0]), "episode_return_mean": v[1] / max(v[0], 1),
                    "episode_len_mean": v[2] / max(v[0], 1)}
-        if args.env == "crypto":
+        if env_name == "builder":
+            summary["wins"] = v[3]
+        if env_name == "crypto":
             summary["final_value_mean"] = v[3] / max(v[0], 1)
-
+    del env, tapes
+    torch.cuda.empty_cache()
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return None
 
     peak, peak_src = load_peak()
-    per_launch_ms = ms / max(1, args.steps)  # rank-0 kernel time; the timed region is back-to-back step launches
+    per_launch_ms = ms / max(1, steps)  # rank-0 kernel time; the timed region is back-to-back step launches
     achieved = n * w.bytes / (per_launch_ms * 1e-3) / 1e9
-    api = {"snake": "BatchedSnakeEnv.step_host -> beng_snake_step_host",
-           "crypto": "BatchedCryptoTradingEnv.step_host -> beng_crypto_step_host",
-           "climate": "BatchedSmartClimateEnv.step_host -> beng_climate_step_host",
-           "builder": "BatchedWorldBuilderEnv.step_host -> beng_builder_step_host",
-           "traffic": "BatchedTrafficManagementEnv.step_host -> beng_traffic_step_host"}[args.env]
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
-        "config": workload_config(args, per_gpu=n),
+    traffic, traffic_src = load_traffic(env_name, n)
+    e2e_gbs = (h2d + d2h_full) / e2e_s_per_step / 1e9  # per rank: every rank moves its own buffers
+    return {
+        "value": value, "ms_per_step": ms_max / max(1, steps), "steps": steps, "warmup": warmup,
+        "config": workload_config(args, per_gpu=n, env_name=env_name),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": load_traffic(args.env, n), "peak_source": peak_src,
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": w.bytes,
-                     "kernel": kernel_description(lib, args.env, n), "kernel_ms": per_launch_ms},
+                     # north_star's literal definition: ncu-measured DRAM bytes against "about 8 TB/s"
+                     "frac_ncu_dram_of_nominal_8tbs": (traffic / (per_launch_ms * 1e-3) / 8e12) if traffic else None,
+                     "kernel": kernel_description(lib, env_name, n), "kernel_ms": per_launch_ms},
         "e2e": {"value": e2e_full, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_full,
-                "steps": e2e_steps, "api": api + " (pinned host buffers, synchronous per step, full observation "
-                                                 "copied back)"},
+                "steps": e2e_steps, "api": API_NAMES[env_name] + " (pinned host buffers, synchronous per step, full "
+                                                                  "observation copied back)",
+                "pcie_gbs": e2e_gbs, "pcie_ceiling_gbs": {"d2h": link_d2h, "h2d": link_h2d},
+                "pcie_frac": e2e_gbs / link_d2h if link_d2h else None,
+                "pcie_note": "per-rank host<->device bytes per second inside the e2e loop (kernel time included) against "
+                             "a plain pinned cudaMemcpyAsync D2H of the observation buffer measured in this run"
+                             + (" with all ranks copying at once (min over ranks)" if world > 1 else ""),
+                "numa_bound": ctx["numa_bound"]},
         "e2e_obs_on_device": {"value": e2e_lite, "unit": UNIT, "h2d_bytes_per_step": h2d,
                               "d2h_bytes_per_step": d2h_lite,
                               "note": "same call with obs_host=NULL: reward/terminated/info to host, observation "
@@ -547,17 +610,75 @@ def run_b200_arm(args):
         "clocks": sampler.summary(),
         "episodes": summary,
     }
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("NCCL_DEBUG_FILE"):
+        # NCCL's banner and communicator lines would precede the JSON line on stdout: send them to stderr instead,
+        # where whoever asked for them (the driver's rank check) still sees every "comm ... nranks N" line.
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+
+    import custom_gymnasium_environments_b200 as pkg
+    from custom_gymnasium_environments_b200.dist import init_process_group
+
+    rank, local_rank, world = init_process_group()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    numa_bound, prev_affinity = pin_to_gpu_numa_node(local_rank)
+    ctx = {"torch": torch, "dist": dist, "pkg": pkg, "lib": pkg._lib.load(), "args": args, "rank": rank,
+           "local_rank": local_rank, "world": world, "dev": dev, "numa_bound": numa_bound}
+    if world > 1:  # one tiny all-reduce up front: creates the NCCL communicator (and its log lines) before any timing
+        dist.all_reduce(torch.zeros(1, device=dev))
+
+    w = WORKLOADS[args.env]
+    head = bench_env(ctx, args.env, args.envs_per_gpu, args.steps, args.warmup, args.e2e_steps)
+    secondary = {}
+    if args.env == "snake" and not args.no_secondary:
+        # BASELINE.json configs[2] and configs[3] in the same driver-run record: shorter device-timed runs of the crypto
+        # and traffic step kernels at their own BASELINE sizes (same timing rules; no CPU leg).
+        for name in ("crypto", "traffic"):
+            blk = bench_env(ctx, name, WORKLOADS[name].envs_per_gpu, min(args.steps, 300), min(args.warmup, 50),
+                            min(args.e2e_steps, 10))
+            if blk is not None:
+                blk.update(metric=METRIC, unit=UNIT, dtype=WORKLOADS[name].dtype, n_gpus=world)
+                secondary[name] = blk
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    line = {"metric": METRIC, "value": head.pop("value"), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head.pop("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": w.dtype, "data": "synthetic"}
+    head.pop("steps"), head.pop("warmup")
+    line.update(head)
+    if secondary:
+        line["secondary"] = secondary
     if world == 1 and not args.no_cpu_baseline:
+        if prev_affinity is not None:
+            os.sched_setaffinity(0, prev_affinity)  # the CPU arm uses every host core again
         cores = os.cpu_count() or 1
-        single = cpu_rate_single(args.env, 2.0)
-        ctx = mp.get_context("fork")
-        with ctx.Pool(cores) as pool_:
+        kind = reference_kind()
+        single = cpu_rate_single(args.env, 2.0, kind)
+        mctx = mp.get_context("fork")
+        with mctx.Pool(cores) as pool_:
             per_proc = max(20, int(single * 10.0))
-            par, wall = cpu_rate_parallel(pool_, args.env, cores, per_proc)
+            par, wall = cpu_rate_parallel(pool_, args.env, cores, per_proc, kind)
         line["cpu_baseline"] = {
-            "value": par, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": port_description(args.env, cores, per_proc) + f" ({wall:.1f} s wall)",
+            "value": par, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": cpu_arm_description(args.env, kind, cores, per_proc) + f" ({wall:.1f} s wall)",
             "single_core_value": single, "c_oracle_single_thread_value": c_oracle_rate(args.env)}
+        if kind == "reference":
+            line["cpu_baseline"]["port_single_core_value"] = cpu_rate_single(args.env, 1.0, "port")
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -577,6 +698,8 @@ def main():
     ap.add_argument("--action-pool", type=int, default=256, help="distinct pre-generated action steps kept in HBM")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="snake only: skip the crypto and traffic blocks that the default run appends as `secondary`")
     ap.add_argument("--no-l2-flush", action="store_true", help="traffic only: time back-to-back steps (L2-warm)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

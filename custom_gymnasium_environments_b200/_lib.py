@@ -36,7 +36,7 @@ class CryptoParams(C.Structure):
 
 
 class CryptoState(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("scal", "meta", "ep_return", "close", "ohlv", "scratch")]
+    _fields_ = [(n, C.c_void_p) for n in ("scal", "meta", "ep_return", "close", "ohlv")]
 
 
 class CryptoIO(C.Structure):

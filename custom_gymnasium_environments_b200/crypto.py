@@ -89,8 +89,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
             self._meta = z(2, n, dt=torch.int32)         # step | regime<<16 | flags<<24 ; rng counter
             self._ep_return = z(n, dt=torch.float64)
             self._close = z(HISTORY, n, dt=torch.float64)
-            self._ohlv = z(HISTORY, 4, n, dt=torch.float32)
-            self._scratch = z(12, n, dt=torch.float32)   # per-step hand-over between the two step kernels
+            self._ohlv = z(HISTORY, n, 4, dt=torch.float32)   # open, high, low, volume: one 16-byte record per env
             # outputs
             self.obs = z(n, OBS_DIM, dt=torch.float32)
             self.reward = z(n, dt=torch.float32)
@@ -105,7 +104,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
             self.stats = z(4, dt=torch.float64)
             self._actions = z(n, 2, dt=torch.float32) if action_type == "continuous" else z(n, dt=torch.int64)
         self._state = _lib.CryptoState(self._scal.data_ptr(), self._meta.data_ptr(), self._ep_return.data_ptr(),
-                                       self._close.data_ptr(), self._ohlv.data_ptr(), self._scratch.data_ptr())
+                                       self._close.data_ptr(), self._ohlv.data_ptr())
         ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self._io = _lib.CryptoIO(self.obs.data_ptr(), self.reward.data_ptr(), self.terminated.data_ptr(),
                                  self.truncated.data_ptr(), ptr(self.reward64), ptr(self.portfolio_value),
@@ -150,8 +149,8 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
         kept in float32 on the device)."""
         order = [(self.params.window_head + 1 + k) % HISTORY for k in range(HISTORY)]
         close = self._close[order]                       # (50, n)
-        ohlv = self._ohlv[order].to(torch.float64)       # (50, 4, n)
-        cand = torch.stack([ohlv[:, 0], ohlv[:, 1], ohlv[:, 2], close, ohlv[:, 3]], dim=-1)  # (50, n, 5)
+        ohlv = self._ohlv[order].to(torch.float64)       # (50, n, 4)
+        cand = torch.stack([ohlv[..., 0], ohlv[..., 1], ohlv[..., 2], close, ohlv[..., 3]], dim=-1)  # (50, n, 5)
         return cand.permute(1, 0, 2).contiguous()
 
     def _infos(self):

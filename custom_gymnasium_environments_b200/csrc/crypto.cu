@@ -9,20 +9,21 @@
 //   CryptoTradingEnv.reset :301-340, step :342-398, _execute_action :400-447, _execute_buy :449-476,
 //                   _execute_sell :478-503, _get_observation :505-561
 //
-// Design:
-//   * one THREAD per env; every state array is laid out [slot/field][env] so that a warp's accesses are
-//     contiguous (the 50-candle window is read as 250 fully coalesced loads per thread, high ILP);
+// Design (the kernel's own comment below has the details):
+//   * state arrays are [slot/field][env] (env fastest), open/high/low/volume as one 16-byte record per (slot, env),
+//     so every access of a warp is contiguous and 64/128-bit wide;
 //   * the window is a ring over 50 slots with ONE head shared by all envs (params.window_head): a step
 //     overwrites the oldest slot, a reset rewrites all 50 slots in rotation -- heads never diverge between
 //     envs, so the layout stays coalesced whatever the episode boundaries are;
-//   * money, prices and indicators are float64 in the reference's operation order (the MACD is a difference
-//     of two EMAs of ~5e4-magnitude prices: float32 closes would break the 1e-5 tolerance); open/high/low/
-//     volume only feed the observation and are stored and normalised in float32;
-//   * the MACD signal line (an O(n^2) prefix loop in the reference, :94-100) is one forward scan;
-//   * the T x 261 float observation tile is contiguous in global memory: composed in shared memory (row
+//   * money, prices and market state are float64 in the reference's operation order; the closes are kept in float64
+//     (the MACD is a difference of two EMAs of ~5e4-magnitude prices: float32 closes would break the 1e-5
+//     tolerance); open/high/low/volume only feed the observation and are stored and normalised in float32;
+//   * the window is streamed ONCE per step: the threads that normalise it into the observation tile also accumulate
+//     the MACD / signal-line dot products and the close range, and hand the last 20 closes to the RSI / Bollinger code;
+//   * the 32 x 261 float observation tile is contiguous in global memory: composed in shared memory (row
 //     stride 261 words = conflict-free) and drained with one bulk asynchronous copy (cp.async.bulk, UBLKCP).
 //
-// HBM-bound: ~2.4 KB per env-step (window read 1.2 KB + observation write 1.04 KB); no tensor-core work.
+// HBM-bound: ~2.4 KB per env-step (window read 1.4 KB + observation write 1.04 KB); no tensor-core work.
 #include <cfloat>
 #include <cstdint>
 #include <cstdio>
@@ -63,9 +64,9 @@ __device__ __forceinline__ double base_trend(int r) {  // :202-208
 }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-// _update_market_regime, :166-186
-__device__ __forceinline__ void update_regime(Market &m, EnvStream &rng) {
-    const int pick = rng.randint(0, 1);  // random.choice of the two successors
+// _update_market_regime, :166-186, given its two draws: `pick` = random.choice of the two successors, `r` = the
+// random() behind random.uniform(lo, hi) for the new trend strength
+__device__ __forceinline__ void apply_regime(Market &m, int pick, double r) {
     int nr;
     switch (m.regime) {
         case BULL_RUN: nr = pick ? CRASH : SIDEWAYS; break;
@@ -75,20 +76,28 @@ __device__ __forceinline__ void update_regime(Market &m, EnvStream &rng) {
         default: nr = pick ? SIDEWAYS : BULL_RUN; break;
     }
     m.regime = nr;
-    if (nr == BULL_RUN || nr == RECOVERY) m.trend = rng.uniform(0.5, 1.0);
-    else if (nr == BEAR_MARKET || nr == CRASH) m.trend = rng.uniform(-1.0, -0.5);
-    else m.trend = rng.uniform(-0.2, 0.2);
+    double lo, hi;
+    if (nr == BULL_RUN || nr == RECOVERY) lo = 0.5, hi = 1.0;
+    else if (nr == BEAR_MARKET || nr == CRASH) lo = -1.0, hi = -0.5;
+    else lo = -0.2, hi = 0.2;
+    m.trend = lo + (hi - lo) * r;  // == uniform(lo, hi) of the RNG contract
+}
+template <typename RNG>
+__device__ __forceinline__ void update_regime(Market &m, RNG &rng) {
+    const int pick = rng.randint(0, 1);
+    const double r = rng.random53();
+    apply_regime(m, pick, r);
 }
 
-// generate_next_price, :132-164, and _update_market_psychology, :213-221
-__device__ __forceinline__ double next_price(const beng_crypto_params &p, Market &m, EnvStream &rng, double cur,
-                                             double volume) {
-    if (rng.random53() < 0.01) update_regime(m, rng);
+// The state-dependent part of generate_next_price (:132-164) + _update_market_psychology (:213-221), given the
+// standard-normal deviate z behind np.random.normal(0, volatility) and volume_factor; same operation order as
+// next_price() below (normal(mu, sd) = mu + sd * z in the RNG contract).
+__device__ __forceinline__ double price_update(const beng_crypto_params &p, Market &m, double cur, double z,
+                                               double volume_factor) {
     const double volatility = p.volatility_base * vol_mult(m.regime);
     const double drift = (m.psych - 0.5) * p.market_psychology_factor;
     const double trend = base_trend(m.regime) * m.trend;
-    const double eps = rng.normal(0.0, volatility);
-    const double volume_factor = 1.0 / (1.0 + volume * 0.1);
+    const double eps = 0.0 + volatility * z;
     const double pct = (trend + drift + eps) * volume_factor;
     const double np_ = clipd(cur * (1.0 + pct), p.min_price, p.max_price);
     m.psych += pct * 10.0;
@@ -97,14 +106,20 @@ __device__ __forceinline__ double next_price(const beng_crypto_params &p, Market
     return np_;
 }
 
-__device__ __forceinline__ void store_candle(double *close_arr, float *ohlv_arr, long long n, long long env, int slot,
+// generate_next_price, :132-164, and _update_market_psychology, :213-221
+template <typename RNG>
+__device__ __forceinline__ double next_price(const beng_crypto_params &p, Market &m, RNG &rng, double cur,
+                                             double volume) {
+    if (rng.random53() < 0.01) update_regime(m, rng);
+    const double u1 = rng.random53(), u2 = rng.random53();  // np.random.normal(0, volatility): Box-Muller, RNG contract
+    const double z = sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2);
+    return price_update(p, m, cur, z, 1.0 / (1.0 + volume * 0.1));
+}
+
+__device__ __forceinline__ void store_candle(double *close_arr, float4 *ohlv_arr, long long n, long long env, int slot,
                                              double open, double high, double low, double close, double volume) {
     close_arr[(long long)slot * n + env] = close;
-    float *o = ohlv_arr + ((long long)slot * 4) * n + env;
-    o[0] = (float)open;
-    o[n] = (float)high;
-    o[2 * n] = (float)low;
-    o[3 * n] = (float)volume;
+    ohlv_arr[(long long)slot * n + env] = make_float4((float)open, (float)high, (float)low, (float)volume);
 }
 
 // reset, :301-340: 50 warm-up candles from 50000.0; the newest lands in slot `head`.  Market state carries over.
@@ -114,8 +129,9 @@ __device__ __forceinline__ void store_candle(double *close_arr, float *ohlv_arr,
 struct WarmupResult {
     Market m;
     uint32_t ctr;
+    double last;  // the newest close of the new window
 };
-__device__ __noinline__ WarmupResult warmup_window(double *close_arr, float *ohlv_arr, long long n, long long env,
+__device__ __noinline__ WarmupResult warmup_window(double *close_arr, float4 *ohlv_arr, long long n, long long env,
                                                    int head, beng_crypto_params p, Market m, uint64_t gid,
                                                    uint32_t ctr) {
     EnvStream rng(p.seed, gid, BENG_STREAM_ENV, ctr);
@@ -130,101 +146,113 @@ __device__ __noinline__ WarmupResult warmup_window(double *close_arr, float *ohl
         store_candle(close_arr, ohlv_arr, n, env, slot, open, high, low, price, volume);
         slot = slot + 1 == HIST ? 0 : slot + 1;
     }
-    return WarmupResult{m, rng.ctr};
+    return WarmupResult{m, rng.ctr, price};
 }
 
-// NumPy's pairwise summation order for 8 <= n <= 128 (np.mean / np.std in the reference), n static.
-template <int N>
-__device__ __forceinline__ double np_sum(const double (&v)[N]) {
+// The same reset done by a whole WARP for ONE env (sparse in-step auto-resets: an episode that ends on `value >= 10 x
+// initial` or `value <= 0`).  Run by one lane, the 50-candle warm-up is a ~90 us serial chain, and the step kernel ends
+// when its slowest CTA does: a handful of resets per step doubled the step time.  Here the lanes draw and transform the
+// random numbers of all 50 candles in parallel (lane l: candles l and l+32) -- Philox, Box-Muller, volume factor -- and
+// only the short state chain (regime -> volatility -> price -> psychology, ~12 dependent float64 operations per candle)
+// stays serial; every lane runs it redundantly, so nothing has to be broadcast afterwards.
+// Draw positions: a candle consumes 14 words (volume 2, regime check 2, normal 4, high 2, low 2, open 2) plus 3 when
+// its regime check fires (choice 1, trend 2), so candle k starts at ctr + 14 k + 3 * (changes before k).  The lanes start
+// from "no change anywhere", find the first candle whose check fires, shift everything behind it by 3 words, and
+// repeat (one extra pass per regime change: 0.5 on average).
+// `stage` is 100 doubles of warp-private shared memory, element d at stage[(d >> 4) * 128 + (d & 15)].
+// All 32 lanes call this with identical arguments.  Bit-identical to warmup_window() (tests: sparse-reset rollouts).
+__device__ __noinline__ WarmupResult coop_warmup_window(double *close_arr, float4 *ohlv_arr, long long n, long long env,
+                                                        int head, beng_crypto_params p, Market m, uint64_t gid,
+                                                        uint32_t ctr, double *stage) {
+    const int lane = threadIdx.x & 31;
+    auto at = [&](int d) -> double & { return stage[(d >> 4) * 128 + (d & 15)]; };
+    double volume[2], z[2], vf[2], uh[2], ul[2], uo[2], rt[2] = {0.0, 0.0};
+    int pick[2] = {0, 0};
+    bool fires[2] = {false, false};
+    unsigned long long fired = 0;  // candles whose regime check fires; bits <= resolved are final
+    int resolved = -1, changes = 0;  // candles <= resolved sit at their final draw positions; `changes` fired among them
+    for (;;) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = lane + 32 * h;
+            if (k < HIST && k > resolved) {  // (first pass: every candle; later: the ones behind the new change)
+                EnvStream r(p.seed, gid, BENG_STREAM_ENV, ctr + 14u * (uint32_t)k + 3u * (uint32_t)changes);
+                volume[h] = r.uniform(0.5, 2.0);
+                fires[h] = r.random53() < 0.01;
+                if (fires[h]) {
+                    pick[h] = r.randint(0, 1);
+                    rt[h] = r.random53();
+                }
+                const double u1 = r.random53(), u2 = r.random53();
+                z[h] = sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2);
+                vf[h] = 1.0 / (1.0 + volume[h] * 0.1);
+                uh[h] = r.uniform(1.0, 1.02);
+                ul[h] = r.uniform(0.98, 1.0);
+                uo[h] = r.uniform(0.99, 1.01);
+            }
+        }
+        fired = (unsigned long long)__ballot_sync(0xFFFFFFFFu, fires[0]) |
+                ((unsigned long long)__ballot_sync(0xFFFFFFFFu, lane + 32 < HIST && fires[1]) << 32);
+        const unsigned long long done = resolved < 0 ? 0ull : ((2ull << resolved) - 1ull);  // bits <= resolved
+        const unsigned long long behind = fired & ~done;
+        if (!behind) break;  // nothing fires behind the resolved prefix: every candle is final
+        resolved = __ffsll((long long)behind) - 1;  // the first one that does (its own draws were at the right place)
+        ++changes;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < HIST) {
+            at(k) = z[h];
+            at(HIST + k) = vf[h];
+        }
+    }
+    __syncwarp();
+    double price = 50000.0;
+#pragma unroll 1
+    for (int k = 0; k < HIST; ++k) {
+        if ((fired >> k) & 1ull) {  // warp-uniform
+            const int src = k & 31;
+            const int pk = __shfl_sync(0xFFFFFFFFu, k < 32 ? pick[0] : pick[1], src);
+            const double r = __shfl_sync(0xFFFFFFFFu, k < 32 ? rt[0] : rt[1], src);
+            apply_regime(m, pk, r);
+        }
+        price = price_update(p, m, price, at(k), at(HIST + k));
+        __syncwarp();
+        if (lane == 0) at(k) = price;  // z[k] is consumed: its slot now carries the close
+    }
+    __syncwarp();
+    const int oldest = head + 1 == HIST ? 0 : head + 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = lane + 32 * h;
+        if (k < HIST) {
+            const double c = at(k);
+            int slot = oldest + k;
+            slot = slot >= HIST ? slot - HIST : slot;
+            store_candle(close_arr, ohlv_arr, n, env, slot, c * uo[h], c * uh[h], c * ul[h], c, volume[h]);
+        }
+    }
+    __syncwarp();
+    return WarmupResult{m, ctr + 14u * HIST + 3u * (uint32_t)changes, price};
+}
+
+// NumPy's pairwise summation order for 8 <= n <= 128 (np.mean / np.std in the reference), n static; the values are
+// produced on demand so that the caller never holds all of them in registers.
+template <int N, typename F>
+__device__ __forceinline__ double np_sum(F val) {
     static_assert(N >= 8 && N < 24, "restated for the two sizes the reference uses (14, 20)");
     double r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = v[j];
+    for (int j = 0; j < 8; ++j) r[j] = val(j);
     if (N >= 16) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += v[8 + j];
+        for (int j = 0; j < 8; ++j) r[j] += val(8 + j);
     }
     double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
 #pragma unroll
-    for (int i = (N >= 16 ? 16 : 8); i < N; ++i) res += v[i];
+    for (int i = (N >= 16 ? 16 : 8); i < N; ++i) res += val(i);
     return res;
-}
-
-// Indicator part of _get_observation (:519-559) for one env, plus the normalised close column.
-// `closes` is the CTA's staging area [HIST-1][T] (float64, oldest first) holding the 49 older closes of every env
-// in the tile; `cur` is the newest close.  Writes row[k*5+3] for k < 49 and row[250..260].
-// `close_at(k)` returns the k-th oldest close (k < 49); WRITE_CLOSE_COL selects whether the normalised close column
-// row[k*5+3] is written here.  `row` receives 250.. as row[250+i] when TAIL_ONLY is false, else tail[i] = feature 250+i.
-template <bool WRITE_CLOSE_COL, typename CloseAt>
-__device__ __forceinline__ void compose_indicators(const beng_crypto_params &p, CloseAt close_at, double cur,
-                                                   double cash, double holdings, double psych, float *row,
-                                                   float *tail) {
-    const double inv = 1.0 / cur;
-    const double mf = 2.0 / 13.0, ms = 2.0 / 27.0, mg = 2.0 / 10.0;  // _ema multipliers, :113
-    double ef = 0.0, es = 0.0, sig = 0.0, mx = 0.0, mn = 0.0;
-    double w[20];  // the last 20 closes (Bollinger window; its last 15 give the 14 RSI deltas)
-#pragma unroll
-    for (int k = 0; k < HIST; ++k) {
-        const double c = (k == HIST - 1) ? cur : close_at(k);
-        if (WRITE_CLOSE_COL && k < HIST - 1) row[k * 5 + 3] = (float)(c * inv);  // close / current_price, :513-515
-        if (k == 0) {
-            ef = es = mx = mn = c;  // _ema seeds at prices[0], :114
-        } else {
-            ef = (c * mf) + (ef * (1.0 - mf));  // :116-117
-            es = (c * ms) + (es * (1.0 - ms));
-            if (k == 25) sig = ef - es;                                    // macd_values[0] (prices[:26]), :94-98
-            else if (k > 25) sig = ((ef - es) * mg) + (sig * (1.0 - mg));  // _ema(macd_values, 9), :100
-            mx = c > mx ? c : mx;
-            mn = c < mn ? c : mn;
-        }
-        if (k >= HIST - 20) w[k - (HIST - 20)] = c;
-    }
-
-    const double value = cash + holdings * cur;  // :519-527
-    tail[0] = (float)(cash / p.initial_balance);
-    tail[1] = (float)(holdings * cur / p.initial_balance);
-    tail[2] = (float)(value / p.initial_balance);
-
-    // RSI(14) over the last 14 deltas, :45-61
-    double g[14], l[14];
-#pragma unroll
-    for (int i = 0; i < 14; ++i) {
-        const double d = w[6 + i] - w[5 + i];
-        g[i] = d > 0 ? d : 0.0;
-        l[i] = d < 0 ? -d : 0.0;
-    }
-    const double avg_gain = np_sum(g) / 14.0, avg_loss = np_sum(l) / 14.0;
-    double rsi = 100.0;
-    if (avg_loss != 0) {
-        const double rs = avg_gain / avg_loss;
-        rsi = 100.0 - (100.0 / (1.0 + rs));
-    }
-    tail[3] = (float)(rsi / 100.0);
-
-    // MACD(12, 26, 9) normalised by the close range, :538-547
-    const double macd_line = ef - es, hist = macd_line - sig, range = mx - mn;
-    if (range > 0) {
-        tail[4] = (float)(macd_line / range);
-        tail[5] = (float)(sig / range);
-        tail[6] = (float)(hist / range);
-    } else {
-        tail[4] = tail[5] = tail[6] = 0.0f;
-    }
-
-    // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
-    const double sma = np_sum(w) / 20.0;
-    double sq[20];
-#pragma unroll
-    for (int i = 0; i < 20; ++i) {
-        const double d = w[i] - sma;
-        sq[i] = d * d;
-    }
-    const double sd = sqrt(np_sum(sq) / 20.0);
-    const double upper = sma + (2 * sd), lower = sma - (2 * sd);
-    tail[7] = (float)((upper > lower) ? (cur - lower) / (upper - lower) : 0.5);
-    tail[8] = (float)((sma > 0) ? (upper - lower) / sma : 0.0);
-    tail[9] = (float)((sma > 0) ? (cur - sma) / sma : 0.0);
-    tail[10] = (float)psych;  // :559
 }
 
 // L2-coherent loads (bypass L1) for data another thread of this CTA may have just rewritten.
@@ -233,14 +261,15 @@ __device__ __forceinline__ double ld_cg_f64(const double *p) {
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float ld_cg_f32(const float *p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+__device__ __forceinline__ float4 ld_cg_f32x4(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 
 // _execute_buy, :449-476.  Returns 1 when the order executed.
-__device__ __forceinline__ int do_buy(const beng_crypto_params &p, EnvStream &rng, double &cash, double &holdings,
+template <typename RNG>
+__device__ __forceinline__ int do_buy(const beng_crypto_params &p, RNG &rng, double &cash, double &holdings,
                                       double amount, double price) {
     if (amount <= 0 || cash < amount) return 0;
     const double slippage = price * p.slippage_rate * rng.uniform(0.5, 1.5);
@@ -253,7 +282,8 @@ __device__ __forceinline__ int do_buy(const beng_crypto_params &p, EnvStream &rn
 }
 
 // _execute_sell, :478-503.  Returns 2 when the order executed.
-__device__ __forceinline__ int do_sell(const beng_crypto_params &p, EnvStream &rng, double &cash, double &holdings,
+template <typename RNG>
+__device__ __forceinline__ int do_sell(const beng_crypto_params &p, RNG &rng, double &cash, double &holdings,
                                        double crypto_amount, double price) {
     if (crypto_amount <= 0 || holdings < crypto_amount) return 0;
     const double slippage = price * p.slippage_rate * rng.uniform(0.5, 1.5);
@@ -271,165 +301,220 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// Warp-specialised CTA over a tile of T consecutive envs, 4*T threads:
-//   threads [0, T)        "env" threads, one per env: trade, price walk, new candle, termination, auto-reset, then the
-//                         sequential indicator scans over the closes staged in shared memory;
-//   threads [T, 4T)       "window" threads: at kernel entry they fetch the 49 older candles of the whole tile with many
-//                         independent, fully coalesced loads (the memory-level parallelism of the kernel), stage the
-//                         closes in shared memory and, once the env threads have published 1/close_now, normalise
-//                         open/high/low/volume straight into the observation tile.
-// Two CTA barriers: (A) closes staged + 1/close published, (B) tile complete -> one bulk asynchronous store.
-// An env that auto-resets rewrites its whole window in this launch; it raises a flag and its elements are re-read
-// (L2-coherent) after barrier A.
-template <int T, bool IS_RESET>
-__global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
-    constexpr int OLD = HIST - 1;          // candles that exist before this step
+// ---------------------------------------------------------------------------------------------------------------
+// crypto3 (the default): persistent 256-thread CTAs over 32-env UNITS (unit u = envs [32u, 32u+32)), eight units per
+// round, units strided over the grid (unit = blockIdx + gridDim * j) so that every CTA gets the same number +-1.
+//
+//   phase 1  warp w owns unit j0+w, one lane per env: ONLY the dynamics (trade, Philox draws, Box-Muller price step,
+//            candle, termination, auto-reset) in the reference's float64 operation order.  The step's Philox words are
+//            computed up front -- five blocks, no data-dependent branch -- and parked in shared memory, so a draw is one
+//            LDS at a running index instead of a divergent "is my block cached?" branch per draw.
+//   phase 2  for each of the round's units all eight warps stream its window: thread (e = lane, g = warp) fetches slots
+//            k = g, g+8, ... of env e (35 coalesced L2-coherent loads), normalises them into the 33 KB observation tile
+//            AND accumulates its share of the indicator work:
+//              * MACD line, signal line: an EMA seeded with prices[0] is a LINEAR function of the window, and so is the
+//                reference's EMA-of-MACD-history (:94-100); both are dot products of the 50 closes with constant weight
+//                vectors (c_macd, built at compile time by running the reference's recurrences on unit vectors).  The
+//                weights sum to zero, so the products are taken with (close - newest close), which is exact (Sterbenz)
+//                and keeps the partial sums small.  Thread (e, g) adds its 7 terms; the 8 partials meet in shared memory.
+//              * max/min of the closes for the MACD normalisation: float32 max/min of (close - newest close); the range
+//                is only a divisor of an observation feature (relative error 1.2e-7 against the allowed 1e-5).
+//              * the last 20 closes (Bollinger window; its last 15 give the RSI deltas) are dropped into shared memory.
+//            After one barrier, warps 0..3 finish MACD / RSI / Bollinger / portfolio features for the 32 envs (sums in
+//            float64 and NumPy's pairwise order; the final quotients, which only feed float32 features, in float32),
+//            then one thread drains the tile with a bulk asynchronous copy.
+// What keeps the reference's exact float64 operation order: everything that feeds back into the state (cash, holdings,
+// price walk, psychology, reward).  What does not: the 11 indicator features, which are float32 outputs checked at
+// rtol 1e-5 / atol 1e-6 (tests/test_crypto_gpu.py); their error against the oracle is ~1e-7.
+constexpr int C3_T = 256, C3_SUB = 32, C3_G = C3_T / C3_SUB, C3_PER = (HIST + C3_G - 1) / C3_G;
+constexpr int C3_RNGW = 20;   // Philox words per env-step: <= 3 (block offset) + 2 (slippage) + 2 + 2 + 3 + 4 + 2 + 2
+constexpr int C3_LAST = 20;   // closes kept for Bollinger / RSI
+constexpr int C3_COOP_MAX = 8;  // resets per warp up to which each one is rebuilt by the whole warp
+constexpr int C3_TILE_BYTES = C3_SUB * OBS * (int)sizeof(float);
+static_assert(C3_TILE_BYTES % 128 == 0, "tile buffers stay 128-byte aligned");
+
+struct MacdWeights {
+    double wm[HIST];  // MACD line   = sum_k wm[k] * close[k]   (k = 0 oldest)
+    double wg[HIST];  // signal line = sum_k wg[k] * close[k]
+};
+// Runs TechnicalIndicators.macd (:79-106) / _ema (:108-119) symbolically: wf[k], ws[k] are the coefficients of close[k]
+// in the fast / slow EMA after consuming closes 0..t, sg[k] those of the signal line.
+constexpr MacdWeights make_macd_weights() {
+    MacdWeights w{};
+    const double mf = 2.0 / 13.0, ms = 2.0 / 27.0, mg = 2.0 / 10.0;
+    double wf[HIST] = {}, ws[HIST] = {}, sg[HIST] = {};
+    wf[0] = 1.0;
+    ws[0] = 1.0;
+    for (int t = 1; t < HIST; ++t) {
+        for (int k = 0; k < t; ++k) {
+            wf[k] = wf[k] * (1.0 - mf);
+            ws[k] = ws[k] * (1.0 - ms);
+        }
+        wf[t] = mf;
+        ws[t] = ms;
+        if (t == 25) {
+            for (int k = 0; k < HIST; ++k) sg[k] = wf[k] - ws[k];
+        } else if (t > 25) {
+            for (int k = 0; k < HIST; ++k) sg[k] = (wf[k] - ws[k]) * mg + sg[k] * (1.0 - mg);
+        }
+    }
+    for (int k = 0; k < HIST; ++k) {
+        w.wm[k] = wf[k] - ws[k];
+        w.wg[k] = sg[k];
+    }
+    return w;
+}
+constexpr MacdWeights k_macd_weights = make_macd_weights();
+__constant__ MacdWeights c_macd = k_macd_weights;
+
+// One env's pre-computed Philox words in shared memory (word j of thread t at w[j * C3_T]); same draw -> value maps as
+// EnvStream (beng_rng.cuh, contract in oracle/philox.py).
+struct TableStream {
+    const uint32_t *w;
+    uint32_t pos, ctr;
+    __device__ __forceinline__ uint32_t u32() {
+        const uint32_t v = w[pos * C3_T];
+        ++pos;
+        ++ctr;
+        return v;
+    }
+    __device__ __forceinline__ int randint(int a, int b) { return a + (int)__umulhi(u32(), (uint32_t)(b - a + 1)); }
+    __device__ __forceinline__ double random53() {
+        const uint32_t a = u32() >> 5, b = u32() >> 6;
+        return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+    }
+    __device__ __forceinline__ double uniform(double a, double b) { return a + (b - a) * random53(); }
+    __device__ __forceinline__ double normal(double mu, double sd) {
+        const double u1 = random53(), u2 = random53();
+        return mu + sd * (sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2));
+    }
+};
+
+constexpr size_t crypto3_smem_bytes(int nbuf) {
+    return (size_t)nbuf * C3_TILE_BYTES + (size_t)C3_T * 8 * 4   // cur, 1/cur, cash, holdings
+           + (size_t)C3_T * 8 * 2                                // MACD / signal partials [8][32]
+           + (size_t)C3_LAST * C3_SUB * 8                        // last 20 closes [20][32]
+           + (size_t)C3_T * 4 * 3                                // psychology, max / min partials
+           + (size_t)C3_RNGW * C3_T * 4;                         // Philox words [20][256]
+}
+
+template <bool IS_RESET, int NBUF, bool PREFETCH, int MINB>
+__global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tile = reinterpret_cast<float *>(smem_raw);                                    // [T][261]
-    double *s_close = reinterpret_cast<double *>(smem_raw + (size_t)T * OBS * sizeof(float));  // [49][T]
-    float *s_inv = reinterpret_cast<float *>(s_close + OLD * T);                          // [T]
-    uint8_t *s_reload = reinterpret_cast<uint8_t *>(s_inv + T);                            // [T]
+    float *tiles = reinterpret_cast<float *>(smem_raw);                                   // [NBUF][32][261]
+    double *s_cur = reinterpret_cast<double *>(smem_raw + (size_t)NBUF * C3_TILE_BYTES);  // [256] newest close
+    double *s_invd = s_cur + C3_T;                                                        // [256] 1 / newest close
+    double *s_cash = s_invd + C3_T;
+    double *s_hold = s_cash + C3_T;
+    double *s_pm = s_hold + C3_T;                      // [8][32] MACD-line partials
+    double *s_pg = s_pm + C3_T;                        // [8][32] signal-line partials
+    double *s_last = s_pg + C3_T;                      // [20][32]
+    float *s_psych = reinterpret_cast<float *>(s_last + C3_LAST * C3_SUB);
+    float *s_mx = s_psych + C3_T;                      // [8][32]
+    float *s_mn = s_mx + C3_T;
+    uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_mn + C3_T);  // [20][256]
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long n = a.n;
-    const long long first = (long long)blockIdx.x * T;
-    // slot that holds the newest candle once this call is done
+    const long long n_units = (n + C3_SUB - 1) / C3_SUB;
+    const uint32_t n32 = (uint32_t)n;
     const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
-    const int oldest = head + 1 == HIST ? 0 : head + 1;  // slots oldest .. oldest+48 (mod 50) are the older candles
+    const int oldest = head + 1 == HIST ? 0 : head + 1;
+    const float ib_f = (float)a.p.initial_balance;
+    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
+    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
 
-    bool ended = false;
-    double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
-
-    if (tid >= T) {
-        // ======================================================================== window threads
-        // Thread (q, e): env column e = j % T of the tile, slots k = q, q+3, q+6, ... (q = j / T in 0..2).  Per slot it
-        // fetches open/high/low/volume (held in registers) and the close (staged in shared memory); slot and field
-        // offsets are compile-time, so the address arithmetic is one pointer bump per value.
-        const int j = tid - T;
-        const int e = j % T, q = j / T;
-        constexpr int PER = (OLD + 2) / 3;  // 17 slots per thread
-        const bool col_ok = first + e < n;
-        const float *obase = a.st.ohlv + first + e;
-        const double *cbase = a.st.close + first + e;
-        float v[PER][4];
-        if constexpr (!IS_RESET) {
+    // element offsets (slot * n) of this thread's candles in the [50][n] windows; independent of the unit
+    uint32_t soff[C3_PER];  // 32-bit: check() bounds n below 2^26, so 49 * n < 2^32
 #pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int k = q + 3 * i;
-                if (k < OLD && col_ok) {
-                    int slot = oldest + k;
-                    slot = slot >= HIST ? slot - HIST : slot;
-                    const float *o = obase + (long long)slot * 4 * n;
-                    v[i][0] = o[0];
-                    v[i][1] = o[n];
-                    v[i][2] = o[2 * n];
-                    v[i][3] = o[3 * n];
-                    s_close[k * T + e] = cbase[(long long)slot * n];
+    for (int i = 0; i < C3_PER; ++i) {
+        int slot = oldest + wid + C3_G * i;
+        slot = slot >= HIST ? slot - HIST : slot;
+        soff[i] = (uint32_t)slot * n32;
+    }
+
+    uint32_t it = 0;  // sub-tiles drained so far by this CTA (selects the tile buffer)
+#pragma unroll 1
+    for (long long j0 = 0;; j0 += C3_G) {
+        const long long u_first = (long long)blockIdx.x + (long long)gridDim.x * j0;
+        if (u_first >= n_units) break;  // CTA-uniform
+
+        // --------------------------------------------------------------------------------------- phase 1
+        {
+            const long long u = (long long)blockIdx.x + (long long)gridDim.x * (j0 + wid);
+            const long long env = u * C3_SUB + lane;
+            const bool active = u < n_units && env < n;
+            const uint64_t gid = a.p.env_id_base + (uint64_t)env;
+            bool ended = false, need_reset = false;
+            double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
+            double cash = 0.0, holdings = 0.0, ep_ret = 0.0, rew = 0.0, value = 0.0, price_out = 0.0, cur = 1.0;
+            Market m{SIDEWAYS, 0.0, 0.5};
+            int step = 0, term = 0, trade = 0;
+            uint32_t flags = 0, ctr = 0;
+            bool step_at_limit = false;
+            // ---- (a) state in, one step of the dynamics, termination decision
+            if (active) {
+                // requested together with the state: the old price and the action head the dependency chain
+                double price_pre = 0.0;
+                long long act_pre = 0;
+                float2 actf_pre = make_float2(0.0f, 0.0f);
+                if constexpr (!IS_RESET) {
+                    price_pre = a.st.close[(long long)a.p.window_head * n + env];
+                    if (a.p.action_type == 1) actf_pre = reinterpret_cast<const float2 *>(a.actions)[env];
+                    else act_pre = reinterpret_cast<const long long *>(a.actions)[env];
                 }
-            }
-        }
-        __syncthreads();  // (A)
-        // (envs that rewrote their window re-stage their own closes after the barrier; see the env branch)
-        if (col_ok) {
-            const float inv_f = s_inv[e];
-            const bool reload = IS_RESET || s_reload[e];
-            float *dst = tile + e * OBS + q * 5;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int k = q + 3 * i;
-                if (k < OLD) {
-                    float x0 = v[i][0], x1 = v[i][1], x2 = v[i][2], x3 = v[i][3];
-                    if (reload) {
-                        int slot = oldest + k;
-                        slot = slot >= HIST ? slot - HIST : slot;
-                        const float *o = obase + (long long)slot * 4 * n;
-                        x0 = ld_cg_f32(o);
-                        x1 = ld_cg_f32(o + n);
-                        x2 = ld_cg_f32(o + 2 * n);
-                        x3 = ld_cg_f32(o + 3 * n);
+                const uint32_t meta = a.st.meta[env];
+                ctr = a.st.meta[n + env];
+                cash = a.st.scal[env];
+                holdings = a.st.scal[n + env];
+                m.trend = a.st.scal[2 * n + env];
+                m.psych = a.st.scal[3 * n + env];
+                step = meta & 0xFFFF;
+                m.regime = (meta >> 16) & 0xFF;
+                flags = meta >> 24;
+                ep_ret = a.st.ep_return[env];
+                if constexpr (IS_RESET) {
+                    need_reset = a.mask ? a.mask[env] != 0 : true;
+                    if (need_reset && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
+                        m.regime = SIDEWAYS;
+                        m.trend = 0.0;
+                        m.psych = 0.5;
+                        ctr = 0;
                     }
-                    dst[i * 15 + 0] = x0 * inv_f;  // price_data / current_price, :513-515
-                    dst[i * 15 + 1] = x1 * inv_f;
-                    dst[i * 15 + 2] = x2 * inv_f;
-                    dst[i * 15 + 4] = x3 * inv_f;  // (index 3 is the close, written by the env thread)
-                }
-            }
-        }
-    } else {
-        // ======================================================================== env threads
-        const long long env = first + tid;
-        const bool active = env < n;
-        float *row = tile + tid * OBS;
-        double cash = 0.0, holdings = 0.0, cur = 1.0, rew = 0.0, value = 0.0, price_out = 0.0, ep_ret = 0.0;
-        float nw_o = 0.f, nw_h = 0.f, nw_l = 0.f, nw_v = 0.f;  // newest candle, float32 like the stored window
-        Market m{SIDEWAYS, 0.0, 0.5};
-        int step = 0, term = 0, trade = 0;
-        bool step_at_limit = false;
-        uint32_t flags = 0, ctr = 0;
-        bool reloaded = IS_RESET;
-        if (active) {
-            cash = a.st.scal[env];
-            holdings = a.st.scal[n + env];
-            m.trend = a.st.scal[2 * n + env];
-            m.psych = a.st.scal[3 * n + env];
-            const uint32_t meta = a.st.meta[env];
-            step = meta & 0xFFFF;
-            m.regime = (meta >> 16) & 0xFF;
-            flags = meta >> 24;
-            ctr = a.st.meta[n + env];
-            ep_ret = a.st.ep_return[env];
-
-            bool selected = true;
-            if constexpr (IS_RESET) {
-                if (a.mask) selected = a.mask[env] != 0;
-                if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
-                    m.regime = SIDEWAYS;
-                    m.trend = 0.0;
-                    m.psych = 0.5;
-                    ctr = 0;
-                }
-            }
-            EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
-
-            auto do_reset = [&]() {
-                cash = a.p.initial_balance;
-                holdings = 0.0;
-                step = 0;
-                flags = 0;
-                ep_ret = 0.0;
-                const WarmupResult wr = warmup_window(a.st.close, a.st.ohlv, n, env, head, a.p, m,
-                                                      a.p.env_id_base + (uint64_t)env, rng.ctr);
-                m = wr.m;
-                rng = EnvStream(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, wr.ctr);
-                reloaded = true;
-            };
-
-            if constexpr (IS_RESET) {
-                if (selected) do_reset();
-            } else {
-                if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
-                    // The ring head moved by one slot with this call: rewrite the whole window at the new rotation.
-                    do_reset();
-                    price_out = a.st.close[(long long)head * n + env];
-                    value = cash + holdings * price_out;
+                } else if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
+                    need_reset = true;  // the ring head moved by one slot with this call: whole window at the new rotation
                 } else {
+                    TableStream rng{s_rng + tid, ctr & 3u, ctr};
+                    {
+                        const uint32_t blk0 = ctr >> 2;
+#pragma unroll
+                        for (int b = 0; b < C3_RNGW / 4; ++b) {
+                            const Philox4 r = philox4x32_10(blk0 + b, (uint32_t)gid, (uint32_t)(gid >> 32), BENG_STREAM_ENV,
+                                                            (uint32_t)a.p.seed, (uint32_t)(a.p.seed >> 32));
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) s_rng[(4 * b + q) * C3_T + tid] = r.v[q];
+                        }
+                    }
                     // _execute_action, :400-447
-                    const double price = a.st.close[(long long)a.p.window_head * n + env];
+                    const double price = price_pre;
                     const double initial_value = cash + holdings * price;
-                    if (a.p.action_type == 1) {
-                        const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
+                    // Order side and size first, then ONE inlined copy of each execution routine, so that lanes of a
+                    // warp holding different actions do not walk through separate copies one after the other.
+                    int side = 0;  // 1 = buy `amount` of cash, 2 = sell `amount` of crypto
+                    double amount = 0.0;
+                    if (a.p.action_type == 1) {  // :408-422
+                        const float2 act = actf_pre;
                         const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
                         const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
-                        if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
-                        else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
-                    } else {
-                        const long long act = reinterpret_cast<const long long *>(a.actions)[env];
-                        if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
-                        else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
-                        else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
-                        else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
-                        // anything else is a hold: the reference does not validate (:424-436)
+                        if (buy > sell && buy > 0) side = 1, amount = buy;
+                        else if (sell > 0) side = 2, amount = sell;
+                    } else {  // :424-436; anything outside 1..4 is a hold: the reference does not validate
+                        const long long act = act_pre;
+                        if (act == 1 || act == 2) side = 1, amount = cash * (act == 1 ? 0.05 : 0.2);
+                        else if (act == 3 || act == 4) side = 2, amount = holdings * (act == 3 ? 0.05 : 0.2);
                     }
+                    if (side == 1) trade = do_buy(a.p, rng, cash, holdings, amount, price);
+                    else if (side == 2) trade = do_sell(a.p, rng, cash, holdings, amount, price);
                     const double final_value = cash + holdings * price;
                     rew = final_value - initial_value;  // valued at the OLD price, :440-441
                     if (!trade) rew -= 1.0;             // :444-445
@@ -438,9 +523,10 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
                     const double new_price = next_price(a.p, m, rng, price, volume);
                     const double high = new_price * rng.uniform(1.0, 1.02);
                     const double low = new_price * rng.uniform(0.98, 1.0);
-                    store_candle(a.st.close, a.st.ohlv, n, env, head, price, high, low, new_price, volume);
+                    store_candle(a.st.close, reinterpret_cast<float4 *>(a.st.ohlv), n, env, head, price, high, low,
+                                 new_price, volume);
+                    ctr = rng.ctr;
                     cur = new_price;
-                    nw_o = (float)price; nw_h = (float)high; nw_l = (float)low; nw_v = (float)volume;
                     value = cash + holdings * new_price;
                     price_out = new_price;
                     step = min(step + 1, 65535);
@@ -454,727 +540,274 @@ __global__ void __launch_bounds__(4 * T) crypto_kernel(const CArgs a) {
                         st_val = value;
                         if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
                         if (a.io.ep_length) a.io.ep_length[env] = step;
-                        if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
+                        if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) need_reset = true;
                         else flags |= CFLAG_NEEDS_RESET;
                     }
                 }
             }
-            if (reloaded) {  // newest candle from the (re)written window; same-thread read-after-write
-                cur = a.st.close[(long long)head * n + env];
-                const float *o = a.st.ohlv + ((long long)head * 4) * n + env;
-                nw_o = o[0]; nw_h = o[n]; nw_l = o[2 * n]; nw_v = o[3 * n];
-            }
-            ctr = rng.ctr;
-            s_inv[tid] = (float)(1.0 / cur);
-        }
-        s_reload[tid] = (uint8_t)(active && reloaded && !IS_RESET);
-        __threadfence_block();
-        __syncthreads();  // (A)
-        if (active) {
-            if (reloaded) {  // stage this env's 49 older closes again (its window changed in this launch)
-                for (int k = 0; k < OLD; ++k)
-                    s_close[k * T + tid] = ld_cg_f64(a.st.close + (long long)((oldest + k) % HIST) * n + env);
-            }
-            const float inv_f = s_inv[tid];
-            row[(HIST - 1) * 5 + 0] = nw_o * inv_f;
-            row[(HIST - 1) * 5 + 1] = nw_h * inv_f;
-            row[(HIST - 1) * 5 + 2] = nw_l * inv_f;
-            row[(HIST - 1) * 5 + 3] = (float)(cur * (1.0 / cur));
-            row[(HIST - 1) * 5 + 4] = nw_v * inv_f;
-            compose_indicators<true>(a.p, [&](int k) { return s_close[k * T + tid]; }, cur, cash, holdings, m.psych, row,
-                                     row + 250);
-
-            a.st.scal[env] = cash;
-            a.st.scal[n + env] = holdings;
-            a.st.scal[2 * n + env] = m.trend;
-            a.st.scal[3 * n + env] = m.psych;
-            a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
-            a.st.meta[n + env] = ctr;
-            a.st.ep_return[env] = ep_ret;
-            if constexpr (!IS_RESET) {
-                a.io.reward[env] = (float)rew;
-                a.io.terminated[env] = (uint8_t)term;
-                if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
-                if (a.io.reward64) a.io.reward64[env] = rew;
-                if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
-                if (a.io.current_price) a.io.current_price[env] = price_out;
-                if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
-            }
-        }
-    }
-
-    // drain the observation tile with one bulk asynchronous copy
-    fence_proxy_async_smem();
-    __syncthreads();  // (B)
-    if (tid == 0) {
-        const long long n_here = min((long long)T, n - first);
-        const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
-        const uint32_t bulk = bytes & ~15u;
-        if (bulk) bulk_store_s2g(a.io.obs + first * OBS, tile, bulk);
-        bulk_commit();
-        for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[first * OBS + i] = tile[i];  // ragged last tile
-    }
-
-    if constexpr (!IS_RESET) {
-        if (a.io.stats && tid < T) {
-            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
-            if (done_mask) {  // rare: ~1 step in 1000
-                const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
-                if ((tid & 31) == 0) {
-                    atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
-                    atomicAdd(&a.io.stats[1], r);
-                    atomicAdd(&a.io.stats[2], l);
-                    atomicAdd(&a.io.stats[3], v2);
+            // ---- (b) state, hand-over to phase 2 and per-step outputs of every env that does not reset in this call
+            // (done BEFORE the resets so that nothing of the hot path is live across their calls)
+            auto put_state = [&]() {
+                s_cur[tid] = cur;
+                s_invd[tid] = 1.0 / cur;
+                s_cash[tid] = cash;
+                s_hold[tid] = holdings;
+                s_psych[tid] = (float)m.psych;  // :559
+                a.st.scal[env] = cash;
+                a.st.scal[n + env] = holdings;
+                a.st.scal[2 * n + env] = m.trend;
+                a.st.scal[3 * n + env] = m.psych;
+                a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
+                a.st.meta[n + env] = ctr;
+                a.st.ep_return[env] = ep_ret;
+            };
+            if (active) {
+                if constexpr (IS_RESET) {
+                    if (!need_reset) cur = a.st.close[(long long)head * n + env];  // not selected: window unchanged
+                } else {
+                    a.io.reward[env] = (float)rew;
+                    a.io.terminated[env] = (uint8_t)term;
+                    if (a.io.truncated)
+                        a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
+                    if (a.io.reward64) a.io.reward64[env] = rew;
+                    if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
+                    if (ended || !need_reset) {  // (a NEXT_STEP reset reports the fresh episode's values below)
+                        if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
+                        if (a.io.current_price) a.io.current_price[env] = price_out;
+                    }
                 }
+                if (!need_reset) put_state();
+            }
+            if constexpr (!IS_RESET) {
+                if (a.io.stats) {
+                    const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+                    if (done_mask) {  // rare: a handful of envs per step
+                        const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
+                        if (lane == 0) {
+                            atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
+                            atomicAdd(&a.io.stats[1], r);
+                            atomicAdd(&a.io.stats[2], l);
+                            atomicAdd(&a.io.stats[3], v2);
+                        }
+                    }
+                }
+            }
+            // ---- (c) resets (:301-340).  A few per warp: the whole warp rebuilds each window together (see
+            // coop_warmup_window); many (reset(), or a batch whose episodes all end on the same step): one lane per env.
+            const unsigned reset_mask = __ballot_sync(0xFFFFFFFFu, need_reset);
+            if (reset_mask) {
+                WarmupResult wr{m, ctr, cur};
+                float4 *ohlv4 = reinterpret_cast<float4 *>(a.st.ohlv);
+                if (IS_RESET || __popc(reset_mask) > C3_COOP_MAX) {
+                    if (need_reset) wr = warmup_window(a.st.close, ohlv4, n, env, head, a.p, m, gid, ctr);
+                } else {
+                    __syncwarp();  // every lane is done with its Philox words: their shared-memory rows become the stage
+                    double *stage = reinterpret_cast<double *>(s_rng + wid * C3_SUB);
+                    for (unsigned rest = reset_mask; rest; rest &= rest - 1) {
+                        const int src = __ffs(rest) - 1;
+                        Market ms;
+                        ms.regime = __shfl_sync(0xFFFFFFFFu, m.regime, src);
+                        ms.trend = __shfl_sync(0xFFFFFFFFu, m.trend, src);
+                        ms.psych = __shfl_sync(0xFFFFFFFFu, m.psych, src);
+                        const uint32_t ctr_s = __shfl_sync(0xFFFFFFFFu, ctr, src);
+                        const long long env_s = u * C3_SUB + src;
+                        const WarmupResult w1 = coop_warmup_window(a.st.close, ohlv4, n, env_s, head, a.p, ms,
+                                                                   a.p.env_id_base + (uint64_t)env_s, ctr_s, stage);
+                        if (lane == src) wr = w1;
+                    }
+                }
+                if (need_reset) {
+                    cash = a.p.initial_balance;
+                    holdings = 0.0;
+                    step = 0;
+                    flags = 0;
+                    ep_ret = 0.0;
+                    m = wr.m;
+                    ctr = wr.ctr;
+                    cur = wr.last;
+                    put_state();
+                    if constexpr (!IS_RESET) {
+                        if (!ended) {  // NEXT_STEP: this call only delivers the reset observation
+                            if (a.io.portfolio_value) a.io.portfolio_value[env] = cash;
+                            if (a.io.current_price) a.io.current_price[env] = cur;
+                        }
+                    }
+                }
+            }
+        }
+        __threadfence();  // this step's candle (and a reset's whole window) must be in L2 before phase 2 reads it
+        __syncthreads();
+
+        // --------------------------------------------------------------------------------------- phase 2
+        const int e = lane, g = wid;
+        float4 x[C3_PER];
+        double c[C3_PER];
+        auto fetch = [&](int sub, float4 (&xo)[C3_PER], double (&co)[C3_PER]) {
+            const long long u = (long long)blockIdx.x + (long long)gridDim.x * (j0 + sub);
+            const long long env = u * C3_SUB + e;
+            if (sub < C3_G && u < n_units && env < n) {
+                const float4 *obase = reinterpret_cast<const float4 *>(a.st.ohlv) + env;
+                const double *cbase = a.st.close + env;
+#pragma unroll
+                for (int i = 0; i < C3_PER; ++i) {
+                    if (g + C3_G * i < HIST) {
+                        xo[i] = ld_cg_f32x4(obase + soff[i]);  // one 128-bit load: open, high, low, volume
+                        co[i] = ld_cg_f64(cbase + soff[i]);
+                    }
+                }
+            }
+        };
+        if constexpr (PREFETCH) fetch(0, x, c);
+#pragma unroll 1
+        for (int sub = 0; sub < C3_G; ++sub, ++it) {
+            const long long u = (long long)blockIdx.x + (long long)gridDim.x * (j0 + sub);
+            if (u >= n_units) break;  // CTA-uniform
+            const long long sub_first = u * C3_SUB;
+            const long long env = sub_first + e;
+            const int le = sub * C3_SUB + e;  // where phase 1 left this env's values
+            float *tile = tiles + (NBUF == 2 ? (it & 1u) : 0u) * (C3_SUB * OBS);
+            if constexpr (!PREFETCH) fetch(sub, x, c);
+            if constexpr (NBUF == 1) {
+                if (it > 0) {  // the previous bulk copy must have read the (single) tile buffer
+                    if (tid == 0) bulk_wait_read<0>();
+                    __syncthreads();
+                }
+            }
+            float *dst = tile + e * OBS;
+            if (env < n) {
+                const double cur = s_cur[le], inv_d = s_invd[le];
+                const float inv_f = (float)inv_d;
+                double pm = 0.0, pg = 0.0;
+                float mx = 0.0f, mn = 0.0f;  // (the newest close itself contributes 0)
+#pragma unroll
+                for (int i = 0; i < C3_PER; ++i) {
+                    const int k = g + C3_G * i;
+                    if (k < HIST) {
+                        dst[k * 5 + 0] = x[i].x * inv_f;  // price_data / current_price, :513-515
+                        dst[k * 5 + 1] = x[i].y * inv_f;
+                        dst[k * 5 + 2] = x[i].z * inv_f;
+                        dst[k * 5 + 3] = (float)(c[i] * inv_d);
+                        dst[k * 5 + 4] = x[i].w * inv_f;
+                        const double d = c[i] - cur;
+                        pm = __fma_rn(c_macd.wm[k], d, pm);
+                        pg = __fma_rn(c_macd.wg[k], d, pg);
+                        const float df = (float)d;
+                        mx = fmaxf(mx, df);
+                        mn = fminf(mn, df);
+                        if (k >= HIST - C3_LAST) s_last[(k - (HIST - C3_LAST)) * C3_SUB + e] = c[i];
+                    }
+                }
+                s_pm[g * C3_SUB + e] = pm;
+                s_pg[g * C3_SUB + e] = pg;
+                s_mx[g * C3_SUB + e] = mx;
+                s_mn[g * C3_SUB + e] = mn;
+            }
+            if constexpr (PREFETCH) fetch(sub + 1, x, c);  // next unit's loads go out before the hand-over below
+            __syncthreads();
+            if (env < n) {
+                if (g == 0) {  // MACD(12, 26, 9) normalised by the close range, :538-547
+                    double pm = 0.0, pg = 0.0;
+                    float mx = 0.0f, mn = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < C3_G; ++q) {
+                        pm += s_pm[q * C3_SUB + e];
+                        pg += s_pg[q * C3_SUB + e];
+                        mx = fmaxf(mx, s_mx[q * C3_SUB + e]);
+                        mn = fminf(mn, s_mn[q * C3_SUB + e]);
+                    }
+                    const float range = mx - mn;
+                    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
+                    if (range > 0.0f) {
+                        f0 = __fdiv_rn((float)pm, range);
+                        f1 = __fdiv_rn((float)pg, range);
+                        f2 = __fdiv_rn((float)(pm - pg), range);
+                    }
+                    dst[254] = f0;
+                    dst[255] = f1;
+                    dst[256] = f2;
+                } else if (g == 1) {  // RSI(14) over the last 14 deltas, :45-61; rsi/100 = gain / (gain + loss)
+                    const double *wl = s_last + 5 * C3_SUB + e;  // the last 15 closes
+                    auto delta = [&](int i) { return wl[(i + 1) * C3_SUB] - wl[i * C3_SUB]; };
+                    const double sg = np_sum<14>([&](int i) { const double d = delta(i); return d > 0 ? d : 0.0; });
+                    const double sl = np_sum<14>([&](int i) { const double d = delta(i); return d < 0 ? -d : 0.0; });
+                    dst[253] = (sl != 0) ? __fdiv_rn((float)sg, (float)(sg + sl)) : 1.0f;
+                } else if (g == 2) {  // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
+                    const double *wl = s_last + e;
+                    const double sma = np_sum<C3_LAST>([&](int i) { return wl[i * C3_SUB]; }) / 20.0;
+                    const double var = np_sum<C3_LAST>([&](int i) { const double d = wl[i * C3_SUB] - sma; return d * d; });
+                    const double sd = sqrt(var / 20.0);
+                    const double upper = sma + (2 * sd), lower = sma - (2 * sd), cur = wl[(C3_LAST - 1) * C3_SUB];
+                    const float width = (float)(upper - lower), mid = (float)sma;
+                    dst[257] = (upper > lower) ? __fdiv_rn((float)(cur - lower), width) : 0.5f;
+                    dst[258] = (sma > 0) ? __fdiv_rn(width, mid) : 0.0f;
+                    dst[259] = (sma > 0) ? __fdiv_rn((float)(cur - sma), mid) : 0.0f;
+                } else if (g == 3) {  // portfolio features :519-527, psychology :559
+                    const double cash = s_cash[le], hv = s_hold[le] * s_cur[le];
+                    dst[250] = __fdiv_rn((float)cash, ib_f);
+                    dst[251] = __fdiv_rn((float)hv, ib_f);
+                    dst[252] = __fdiv_rn((float)(cash + hv), ib_f);
+                    dst[260] = s_psych[le];
+                }
+            }
+            fence_proxy_async_smem();
+            if constexpr (NBUF == 2) {
+                if (tid == 0) bulk_wait_read<0>();  // the copy issued one sub-tile ago has read the other buffer
+            }
+            __syncthreads();
+            if (tid == 0) {
+                const long long n_here = min((long long)C3_SUB, n - sub_first);
+                const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
+                const uint32_t bulk = bytes & ~15u;
+                if (bulk) bulk_store_s2g(a.io.obs + sub_first * OBS, tile, bulk);
+                bulk_commit();
+                for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[sub_first * OBS + i] = tile[i];  // ragged tail
             }
         }
     }
     if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the copy engine's reads
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Two-phase CTA (the default): 256 threads own 256 consecutive envs.
-//   phase 1  one thread per env: trade, price walk, candle, termination, auto-reset and the indicator scans, closes
-//            read straight from global memory (coalesced over envs).  No observation staging is needed here, so 512
-//            env threads are resident per SM (4x the warp-specialised kernel above) to hide the long serial float64
-//            chain.  Each thread leaves 1/close and its 11 indicator features in shared memory.
-//   phase 2  all 256 threads stream the window of eight 32-env sub-tiles: thread (e = tid % 32, g = tid / 32) handles
-//            slots k = g, g+8, ... of env e, normalises open/high/low/close/volume into a double-buffered 33 KB
-//            observation tile, which one thread drains with a bulk asynchronous copy while the next sub-tile is built.
-// Window reads in phase 2 are L2-coherent (ld.global.cg): an env that auto-reset rewrote its window in phase 1.
-constexpr int C2_ENVS = 256, C2_SUB = 32, C2_GROUPS = C2_ENVS / C2_SUB;
-
-template <bool IS_RESET>
-__global__ void __launch_bounds__(C2_ENVS, 2) crypto2_kernel(const CArgs a) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);                     // [2][32][261]
-    float *s_tail = tiles + 2 * C2_SUB * OBS;                               // [256][11]
-    float *s_inv = s_tail + C2_ENVS * 11;                                   // [256]
-    double *s_invd = reinterpret_cast<double *>(s_inv + C2_ENVS);           // [256]
-
-    const int tid = threadIdx.x;
-    const long long n = a.n;
-    const long long first = (long long)blockIdx.x * C2_ENVS;
-    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
-    const int oldest = head + 1 == HIST ? 0 : head + 1;
-    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
-    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
-
-    // ------------------------------------------------------------------------------------------- phase 1
-    bool ended = false;
-    double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
-    {
-        const long long env = first + tid;
-        if (env < n) {
-            // requested together with the state (they are only used on the ordinary step path, but waiting for the flags
-            // to arrive before asking for them would put a second memory round trip at the head of the chain)
-            double price_pre = 0.0;
-            long long act_pre = 0;
-            float2 actf_pre = make_float2(0.0f, 0.0f);
-            if constexpr (!IS_RESET) {
-                price_pre = a.st.close[(long long)a.p.window_head * n + env];
-                if (a.p.action_type == 1) actf_pre = reinterpret_cast<const float2 *>(a.actions)[env];
-                else act_pre = reinterpret_cast<const long long *>(a.actions)[env];
-            }
-            double cash = a.st.scal[env], holdings = a.st.scal[n + env];
-            Market m;
-            m.trend = a.st.scal[2 * n + env];
-            m.psych = a.st.scal[3 * n + env];
-            const uint32_t meta = a.st.meta[env];
-            int step = meta & 0xFFFF;
-            m.regime = (meta >> 16) & 0xFF;
-            uint32_t flags = meta >> 24;
-            uint32_t ctr = a.st.meta[n + env];
-            double ep_ret = a.st.ep_return[env];
-            bool selected = true;
-            if constexpr (IS_RESET) {
-                if (a.mask) selected = a.mask[env] != 0;
-                if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
-                    m.regime = SIDEWAYS;
-                    m.trend = 0.0;
-                    m.psych = 0.5;
-                    ctr = 0;
-                }
-            }
-            EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
-            double rew = 0.0, value = 0.0, price_out = 0.0, cur = 0.0;
-            int term = 0, trade = 0;
-            bool step_at_limit = false;
-            bool rewrote = false;
-
-            auto do_reset = [&]() {
-                cash = a.p.initial_balance;
-                holdings = 0.0;
-                step = 0;
-                flags = 0;
-                ep_ret = 0.0;
-                const WarmupResult wr = warmup_window(a.st.close, a.st.ohlv, n, env, head, a.p, m,
-                                                      a.p.env_id_base + (uint64_t)env, rng.ctr);
-                m = wr.m;
-                rng = EnvStream(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, wr.ctr);
-                rewrote = true;
-            };
-
-            if constexpr (IS_RESET) {
-                if (selected) do_reset();
-                else rewrote = true;  // (just re-read the newest close below)
-            } else {
-                if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
-                    do_reset();  // the ring head moved by one slot with this call: whole window at the new rotation
-                    price_out = a.st.close[(long long)head * n + env];
-                    value = cash + holdings * price_out;
-                } else {
-                    // _execute_action, :400-447
-                    const double price = price_pre;
-                    const double initial_value = cash + holdings * price;
-                    if (a.p.action_type == 1) {
-                        const float2 act = actf_pre;
-                        const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
-                        const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
-                        if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
-                        else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
-                    } else {
-                        const long long act = act_pre;
-                        if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
-                        else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
-                        else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
-                        else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
-                        // anything else is a hold: the reference does not validate (:424-436)
-                    }
-                    const double final_value = cash + holdings * price;
-                    rew = final_value - initial_value;  // valued at the OLD price, :440-441
-                    if (!trade) rew -= 1.0;             // :444-445
-                    // next candle, :348-365
-                    const double volume = rng.uniform(0.5, 2.0);
-                    const double new_price = next_price(a.p, m, rng, price, volume);
-                    const double high = new_price * rng.uniform(1.0, 1.02);
-                    const double low = new_price * rng.uniform(0.98, 1.0);
-                    store_candle(a.st.close, a.st.ohlv, n, env, head, price, high, low, new_price, volume);
-                    cur = new_price;
-                    value = cash + holdings * new_price;
-                    price_out = new_price;
-                    step = min(step + 1, 65535);
-                    step_at_limit = step >= a.p.max_steps;
-                    term = step_at_limit || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
-                    ep_ret += rew;
-                    if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
-                        ended = true;
-                        st_ret = ep_ret;
-                        st_len = (double)step;
-                        st_val = value;
-                        if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
-                        if (a.io.ep_length) a.io.ep_length[env] = step;
-                        if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
-                        else flags |= CFLAG_NEEDS_RESET;
-                    }
-                }
-            }
-            if (rewrote) cur = a.st.close[(long long)head * n + env];  // same-thread read-after-write
-
-            // indicator features 250..260; the 49 older closes come straight from global memory
-            const double *cbase = a.st.close + env;
-            compose_indicators<false>(
-                a.p,
-                [&](int k) {
-                    int slot = oldest + k;
-                    slot = slot >= HIST ? slot - HIST : slot;
-                    return cbase[(long long)slot * n];
-                },
-                cur, cash, holdings, m.psych, nullptr, s_tail + tid * 11);
-            const double inv = 1.0 / cur;
-            s_invd[tid] = inv;
-            s_inv[tid] = (float)inv;
-
-            a.st.scal[env] = cash;
-            a.st.scal[n + env] = holdings;
-            a.st.scal[2 * n + env] = m.trend;
-            a.st.scal[3 * n + env] = m.psych;
-            a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
-            a.st.meta[n + env] = rng.ctr;
-            a.st.ep_return[env] = ep_ret;
-            if constexpr (!IS_RESET) {
-                a.io.reward[env] = (float)rew;
-                a.io.terminated[env] = (uint8_t)term;
-                if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
-                if (a.io.reward64) a.io.reward64[env] = rew;
-                if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
-                if (a.io.current_price) a.io.current_price[env] = price_out;
-                if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
-            }
-        }
-        if constexpr (!IS_RESET) {
-            if (a.io.stats) {
-                const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
-                if (done_mask) {  // rare: ~1 step in 1000
-                    const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
-                    if ((tid & 31) == 0) {
-                        atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
-                        atomicAdd(&a.io.stats[1], r);
-                        atomicAdd(&a.io.stats[2], l);
-                        atomicAdd(&a.io.stats[3], v2);
-                    }
-                }
-            }
-        }
-    }
-    __threadfence();  // this step's candle (and a reset's whole window) must be in L2 before phase 2 reads it
-    __syncthreads();
-
-    // ------------------------------------------------------------------------------------------- phase 2
-    const int e = tid % C2_SUB, g = tid / C2_SUB;
-    constexpr int PER = (HIST + C2_GROUPS - 1) / C2_GROUPS;  // 7 slots per thread
-    // Element offsets of this thread's slots (they do not depend on the sub-tile; only the env column moves).
-    long long ooff[PER], coff[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int slot = oldest + g + C2_GROUPS * i;
-        slot = slot >= HIST ? slot - HIST : slot;
-        ooff[i] = (long long)slot * 4 * n;
-        coff[i] = (long long)slot * n;
-    }
-    // Software pipeline over the sub-tiles: the 35 window values of sub-tile s+1 are requested before sub-tile s is
-    // fenced, barriered and handed to the copy engine, so their latency overlaps that hand-over.
-    float x[PER][4], xn[PER][4];
-    double c[PER], cn[PER];
-    auto fetch = [&](int sub, float (&xo)[PER][4], double (&co)[PER]) {
-        const long long env = first + (long long)sub * C2_SUB + e;
-        if (sub < C2_GROUPS && env < n) {
-            const float *obase = a.st.ohlv + env;
-            const double *cbase = a.st.close + env;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                if (g + C2_GROUPS * i < HIST) {
-                    const float *o = obase + ooff[i];
-                    xo[i][0] = ld_cg_f32(o);
-                    xo[i][1] = ld_cg_f32(o + n);
-                    xo[i][2] = ld_cg_f32(o + 2 * n);
-                    xo[i][3] = ld_cg_f32(o + 3 * n);
-                    co[i] = ld_cg_f64(cbase + coff[i]);
-                }
-            }
-        }
-    };
-    fetch(0, x, c);
-#pragma unroll 1
-    for (int sub = 0; sub < C2_GROUPS; ++sub) {
-        const long long sub_first = first + (long long)sub * C2_SUB;
-        if (sub_first >= n) break;  // CTA-uniform
-        float *tile = tiles + (sub & 1) * (C2_SUB * OBS);
-        const long long env = sub_first + e;
-        const int le = sub * C2_SUB + e;  // env index within the CTA
-        if (sub >= 2) {  // the bulk copy that used this buffer two sub-tiles ago must have read it
-            if (tid == 0) bulk_wait_read<1>();
-            __syncthreads();
-        }
-        if (env < n) {
-            const float inv_f = s_inv[le];
-            const double inv_d = s_invd[le];
-            float *dst = tile + e * OBS;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int k = g + C2_GROUPS * i;
-                if (k < HIST) {
-                    dst[k * 5 + 0] = x[i][0] * inv_f;  // price_data / current_price, :513-515
-                    dst[k * 5 + 1] = x[i][1] * inv_f;
-                    dst[k * 5 + 2] = x[i][2] * inv_f;
-                    dst[k * 5 + 3] = (float)(c[i] * inv_d);
-                    dst[k * 5 + 4] = x[i][3] * inv_f;
-                }
-            }
-            // the 11 indicator features: groups 0..7 copy them (11 values over 8 groups)
-            for (int j = g; j < 11; j += C2_GROUPS) dst[250 + j] = s_tail[le * 11 + j];
-        }
-        fetch(sub + 1, xn, cn);  // next sub-tile's loads go out before the hand-over below
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            const long long n_here = min((long long)C2_SUB, n - sub_first);
-            const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
-            const uint32_t bulk = bytes & ~15u;
-            if (bulk) bulk_store_s2g(a.io.obs + sub_first * OBS, tile, bulk);
-            bulk_commit();
-            for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[sub_first * OBS + i] = tile[i];  // ragged tail
-        }
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            x[i][0] = xn[i][0]; x[i][1] = xn[i][1]; x[i][2] = xn[i][2]; x[i][3] = xn[i][3];
-            c[i] = cn[i];
-        }
-    }
-    if (tid == 0) bulk_wait_read<0>();
-}
-
-constexpr size_t crypto2_smem_bytes() {
-    return (size_t)2 * C2_SUB * OBS * sizeof(float) + (size_t)C2_ENVS * 11 * sizeof(float) + C2_ENVS * sizeof(float) +
-           C2_ENVS * sizeof(double);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Split step (BENG_CRYPTO_MODE=split; not the default, see launch()): two kernels, each shaped for what bounds it.
-//   crypto_dyn_kernel  one thread per env, no shared memory: trade, price walk, candle, termination, auto-reset and
-//                      the indicator scans (closes straight from global memory, coalesced over envs).  Leaves the 11
-//                      indicator features and 1/close in st.scratch [12][n].
-//   crypto_obs_kernel  persistent streaming kernel (like the snake step): per 32-env tile each thread fetches 35
-//                      window values one tile ahead, normalises them into one of three 33 KB tile buffers, and one
-//                      thread drains the tile with a bulk asynchronous copy.  Launched with PDL behind the first.
-template <int N, typename F>
-__device__ __forceinline__ double np_sum_stream(F val) {  // NumPy pairwise order for N in {14, 20}, values on demand
-    double r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = val(j);
-    if (N >= 16) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += val(8 + j);
-    }
-    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-#pragma unroll
-    for (int i = (N >= 16 ? 16 : 8); i < N; ++i) res += val(i);
-    return res;
-}
-
-template <bool IS_RESET>
-__global__ void __launch_bounds__(256, 2) crypto_dyn_kernel(const CArgs a) {
-    const long long n = a.n;
-    const long long env = (long long)blockIdx.x * 256 + threadIdx.x;
-    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
-    const int oldest = head + 1 == HIST ? 0 : head + 1;
-    pdl_launch_dependents();
-    pdl_wait();  // the previous step's observation kernel still reads the window slot this step overwrites
-
-    bool ended = false;
-    double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
-    if (env < n) {
-        double cash = a.st.scal[env], holdings = a.st.scal[n + env];
-        Market m;
-        m.trend = a.st.scal[2 * n + env];
-        m.psych = a.st.scal[3 * n + env];
-        const uint32_t meta = a.st.meta[env];
-        int step = meta & 0xFFFF;
-        m.regime = (meta >> 16) & 0xFF;
-        uint32_t flags = meta >> 24;
-        uint32_t ctr = a.st.meta[n + env];
-        double ep_ret = a.st.ep_return[env];
-        bool selected = true;
-        if constexpr (IS_RESET) {
-            if (a.mask) selected = a.mask[env] != 0;
-            if (selected && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
-                m.regime = SIDEWAYS;
-                m.trend = 0.0;
-                m.psych = 0.5;
-                ctr = 0;
-            }
-        }
-        EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
-        double rew = 0.0, value = 0.0, price_out = 0.0, cur = 0.0;
-        int term = 0, trade = 0;
-        bool step_at_limit = false, rewrote = false;
-
-        auto do_reset = [&]() {
-            cash = a.p.initial_balance;
-            holdings = 0.0;
-            step = 0;
-            flags = 0;
-            ep_ret = 0.0;
-            const WarmupResult wr = warmup_window(a.st.close, a.st.ohlv, n, env, head, a.p, m,
-                                                  a.p.env_id_base + (uint64_t)env, rng.ctr);
-            m = wr.m;
-            rng = EnvStream(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, wr.ctr);
-            rewrote = true;
-        };
-
-        if constexpr (IS_RESET) {
-            if (selected) do_reset();
-            else rewrote = true;  // (just re-read the newest close below)
-        } else {
-            if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
-                do_reset();  // the ring head moved by one slot with this call: whole window at the new rotation
-                price_out = a.st.close[(long long)head * n + env];
-                value = cash + holdings * price_out;
-            } else {
-                // _execute_action, :400-447
-                const double price = a.st.close[(long long)a.p.window_head * n + env];
-                const double initial_value = cash + holdings * price;
-                if (a.p.action_type == 1) {
-                    const float2 act = reinterpret_cast<const float2 *>(a.actions)[env];
-                    const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
-                    const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
-                    if (buy > sell && buy > 0) trade = do_buy(a.p, rng, cash, holdings, buy, price);
-                    else if (sell > 0) trade = do_sell(a.p, rng, cash, holdings, sell, price);
-                } else {
-                    const long long act = reinterpret_cast<const long long *>(a.actions)[env];
-                    if (act == 1) trade = do_buy(a.p, rng, cash, holdings, cash * 0.05, price);
-                    else if (act == 2) trade = do_buy(a.p, rng, cash, holdings, cash * 0.2, price);
-                    else if (act == 3) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.05, price);
-                    else if (act == 4) trade = do_sell(a.p, rng, cash, holdings, holdings * 0.2, price);
-                    // anything else is a hold: the reference does not validate (:424-436)
-                }
-                const double final_value = cash + holdings * price;
-                rew = final_value - initial_value;  // valued at the OLD price, :440-441
-                if (!trade) rew -= 1.0;             // :444-445
-                // next candle, :348-365
-                const double volume = rng.uniform(0.5, 2.0);
-                const double new_price = next_price(a.p, m, rng, price, volume);
-                const double high = new_price * rng.uniform(1.0, 1.02);
-                const double low = new_price * rng.uniform(0.98, 1.0);
-                store_candle(a.st.close, a.st.ohlv, n, env, head, price, high, low, new_price, volume);
-                cur = new_price;
-                value = cash + holdings * new_price;
-                price_out = new_price;
-                step = min(step + 1, 65535);
-                step_at_limit = step >= a.p.max_steps;
-                term = step_at_limit || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
-                ep_ret += rew;
-                if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
-                    ended = true;
-                    st_ret = ep_ret;
-                    st_len = (double)step;
-                    st_val = value;
-                    if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
-                    if (a.io.ep_length) a.io.ep_length[env] = step;
-                    if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) do_reset();
-                    else flags |= CFLAG_NEEDS_RESET;
-                }
-            }
-        }
-        if (rewrote) cur = a.st.close[(long long)head * n + env];  // same-thread read-after-write
-
-        // ---- state, per-step outputs and the cheap features first: frees their registers for the scans below
-        float *sc = a.st.scratch + env;
-        {
-            const double cur_value = cash + holdings * cur;  // :519-527
-            sc[0] = (float)(cash / a.p.initial_balance);
-            sc[n] = (float)(holdings * cur / a.p.initial_balance);
-            sc[2 * n] = (float)(cur_value / a.p.initial_balance);
-            sc[10 * n] = (float)m.psych;        // :559
-            sc[11 * n] = (float)(1.0 / cur);    // hand-over to the observation kernel
-        }
-        a.st.scal[env] = cash;
-        a.st.scal[n + env] = holdings;
-        a.st.scal[2 * n + env] = m.trend;
-        a.st.scal[3 * n + env] = m.psych;
-        a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
-        a.st.meta[n + env] = rng.ctr;
-        a.st.ep_return[env] = ep_ret;
-        if constexpr (!IS_RESET) {
-            a.io.reward[env] = (float)rew;
-            a.io.terminated[env] = (uint8_t)term;
-            if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
-            if (a.io.reward64) a.io.reward64[env] = rew;
-            if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
-            if (a.io.current_price) a.io.current_price[env] = price_out;
-            if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
-        }
-
-        // ---- indicator scans over the 50 closes (oldest first); close k < 49 lives in slot (oldest + k) % 50.
-        // The last 20 closes stay in registers for the Bollinger / RSI windows: re-reading them through L1 with 1024
-        // threads per SM was measured 2x slower (L1 hit rate 41 %) than 512 threads with the window in registers.
-        const double *cbase = a.st.close + env;
-        float tail[11];
-        compose_indicators<false>(
-            a.p,
-            [&](int k) {
-                int slot = oldest + k;
-                slot = slot >= HIST ? slot - HIST : slot;
-                return cbase[(long long)slot * n];
-            },
-            cur, 0.0, 0.0, 0.0, nullptr, tail);
-#pragma unroll
-        for (int j = 3; j < 10; ++j) sc[(long long)j * n] = tail[j];  // RSI, MACD x3, Bollinger x3
-    }
-    if constexpr (!IS_RESET) {
-        if (a.io.stats) {
-            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
-            if (done_mask) {  // rare: ~1 step in 1000
-                const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
-                if ((threadIdx.x & 31) == 0) {
-                    atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
-                    atomicAdd(&a.io.stats[1], r);
-                    atomicAdd(&a.io.stats[2], l);
-                    atomicAdd(&a.io.stats[3], v2);
-                }
-            }
-        }
-    }
-}
-
-constexpr int OBS_SUB = 32, OBS_THREADS = 256, OBS_GROUPS = OBS_THREADS / OBS_SUB, OBS_STAGES = 3;
-
-__global__ void __launch_bounds__(OBS_THREADS, 2) crypto_obs_kernel(const CArgs a, int head) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);  // [OBS_STAGES][32][261]
-    const int tid = threadIdx.x;
-    const int e = tid % OBS_SUB, g = tid / OBS_SUB;
-    const long long n = a.n;
-    const long long n_tiles = (n + OBS_SUB - 1) / OBS_SUB;
-    const int oldest = head + 1 == HIST ? 0 : head + 1;
-    constexpr int PER = (HIST + OBS_GROUPS - 1) / OBS_GROUPS;  // 7 slots per thread
-    long long ooff[PER], coff[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        int slot = oldest + g + OBS_GROUPS * i;
-        slot = slot >= HIST ? slot - HIST : slot;
-        ooff[i] = (long long)slot * 4 * n;
-        coff[i] = (long long)slot * n;
-    }
-    pdl_launch_dependents();
-    pdl_wait();  // everything below reads what the dynamics kernel of this step wrote
-
-    float x[PER][4], xn[PER][4], t0 = 0.f, t1 = 0.f, t0n = 0.f, t1n = 0.f, inv = 0.f, invn = 0.f;
-    double c[PER], cn[PER];
-    auto fetch = [&](long long tile, float (&xo)[PER][4], double (&co)[PER], float &ta, float &tb, float &iv) {
-        const long long env = tile * OBS_SUB + e;
-        if (tile < n_tiles && env < n) {
-            const float *obase = a.st.ohlv + env;
-            const double *cbase = a.st.close + env;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                if (g + OBS_GROUPS * i < HIST) {
-                    const float *o = obase + ooff[i];
-                    xo[i][0] = __ldg(o);
-                    xo[i][1] = __ldg(o + n);
-                    xo[i][2] = __ldg(o + 2 * n);
-                    xo[i][3] = __ldg(o + 3 * n);
-                    co[i] = __ldg(cbase + coff[i]);
-                }
-            }
-            const float *sc = a.st.scratch + env;
-            ta = __ldg(sc + (long long)g * n);                    // features 250 + g        (g = 0..7)
-            tb = (g < 3) ? __ldg(sc + (long long)(g + 8) * n) : 0.f;  // features 258, 259, 260  (g = 0..2)
-            iv = __ldg(sc + 11 * n);
-        }
-    };
-    fetch(blockIdx.x, x, c, t0, t1, inv);
-    int it = 0;
-#pragma unroll 1
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        float *buf = tiles + (size_t)(it % OBS_STAGES) * (OBS_SUB * OBS);
-        const long long first = tile * OBS_SUB;
-        const long long env = first + e;
-        fetch(tile + gridDim.x, xn, cn, t0n, t1n, invn);  // next tile's values, consumed next iteration
-        if (it >= OBS_STAGES) {  // the bulk copy that last used this buffer must have read it
-            if (tid == 0) bulk_wait_read<OBS_STAGES - 1>();
-            __syncthreads();
-        }
-        if (env < n) {
-            float *dst = buf + e * OBS;
-#pragma unroll
-            for (int i = 0; i < PER; ++i) {
-                const int k = g + OBS_GROUPS * i;
-                if (k < HIST) {
-                    dst[k * 5 + 0] = x[i][0] * inv;  // price_data / current_price, :513-515 (volume is divided too)
-                    dst[k * 5 + 1] = x[i][1] * inv;
-                    dst[k * 5 + 2] = x[i][2] * inv;
-                    dst[k * 5 + 3] = (float)(c[i] * (double)inv);
-                    dst[k * 5 + 4] = x[i][3] * inv;
-                }
-            }
-            dst[250 + g] = t0;
-            if (g < 3) dst[258 + g] = t1;
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            const long long n_here = min((long long)OBS_SUB, n - first);
-            const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
-            const uint32_t bulk = bytes & ~15u;
-            if (bulk) bulk_store_s2g(a.io.obs + first * OBS, buf, bulk);
-            bulk_commit();
-            for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[first * OBS + i] = buf[i];  // ragged last tile
-        }
-#pragma unroll
-        for (int i = 0; i < PER; ++i) {
-            x[i][0] = xn[i][0]; x[i][1] = xn[i][1]; x[i][2] = xn[i][2]; x[i][3] = xn[i][3];
-            c[i] = cn[i];
-        }
-        t0 = t0n; t1 = t1n; inv = invn;
-    }
-    if (tid == 0) bulk_wait_read<0>();
-}
-
-template <bool IS_RESET>
-int launch_split(const CArgs &a, cudaStream_t stream) {
-    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
-    cudaError_t e = launch_pdl(crypto_dyn_kernel<IS_RESET>, dim3((unsigned)((a.n + 255) / 256)), dim3(256), 0, stream, a);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+template <bool IS_RESET, int NBUF, bool PREFETCH, int MINB>
+int launch3(const CArgs &a, cudaStream_t stream) {
+    const size_t smem = crypto3_smem_bytes(NBUF);
+    auto kern = crypto3_kernel<IS_RESET, NBUF, PREFETCH, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = (size_t)OBS_STAGES * OBS_SUB * OBS * sizeof(float);
-    e = cudaFuncSetAttribute(crypto_obs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const long long n_tiles = (a.n + OBS_SUB - 1) / OBS_SUB;
-    long long grid = 2LL * device_sm_count();
-    if (grid > n_tiles) grid = n_tiles;
-    // (two-argument kernel: launch through the runtime's variadic form with the PDL attribute)
-    {
-        static const bool use_pdl = getenv("BENG_NO_PDL") == nullptr;
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(OBS_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, crypto_obs_kernel, a, head);
-    }
+    const long long n_units = (a.n + C3_SUB - 1) / C3_SUB;
+    long long grid = (long long)MINB * device_sm_count();
+    if (grid > n_units) grid = n_units;
+    e = launch_pdl(kern, dim3((unsigned)grid), dim3(C3_T), smem, stream, a);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
     return (int)e;
 }
 
 
-template <int T>
-constexpr size_t crypto_smem_bytes() {
-    return (size_t)T * OBS * sizeof(float) + (size_t)(HIST - 1) * T * sizeof(double) + T * sizeof(float) + T;
-}
-
 template <bool IS_RESET>
 int launch(const CArgs &a, cudaStream_t stream) {
-    static int tile_env = -1;
-    if (tile_env < 0) {
-        tile_env = 0;
-        if (const char *e = getenv("BENG_CRYPTO_TILE")) tile_env = atoi(e);
+    // BENG_CRYPTO_VARIANT (read once): 0 = crypto3 two tile buffers + register prefetch, 2 CTAs/SM (default);
+    // 1 = one buffer, no prefetch, 3 CTAs/SM; 2 = two buffers, no prefetch, 2 CTAs/SM; 3 = one buffer, no prefetch,
+    // 4 CTAs/SM.
+    static int variant = -1;
+    if (variant < 0) {
+        const char *v = getenv("BENG_CRYPTO_VARIANT");
+        variant = v ? atoi(v) : 0;
     }
-    // Default: the fused two-phase kernel (237 us/step at 262,144 envs).  BENG_CRYPTO_MODE=split selects the two-kernel
-    // step (277 us: its streaming observation kernel runs at 5.1 TB/s, but the stand-alone dynamics kernel loses the
-    // overlap it enjoys inside the fused kernel); BENG_CRYPTO_TILE=32|64|128 the warp-specialised kernel (381 us).
-    static int split = -1;
-    if (split < 0) {
-        const char *m = getenv("BENG_CRYPTO_MODE");
-        split = (m && m[0] == 's') ? 1 : 0;
+    switch (variant) {
+        case 1: return launch3<IS_RESET, 1, false, 3>(a, stream);
+        case 2: return launch3<IS_RESET, 2, false, 2>(a, stream);
+        case 3: return launch3<IS_RESET, 1, false, 4>(a, stream);
+        default: return launch3<IS_RESET, 2, true, 2>(a, stream);
     }
-    if (split && a.st.scratch) return launch_split<IS_RESET>(a, stream);
-    if (tile_env <= 0) {
-        const size_t smem = crypto2_smem_bytes();
-        auto kern = crypto2_kernel<IS_RESET>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        e = launch_pdl(kern, dim3((unsigned)((a.n + C2_ENVS - 1) / C2_ENVS)), dim3(C2_ENVS), smem, stream, a);
-        g_launch_count.fetch_add(1, std::memory_order_relaxed);
-        return (int)e;
-    }
-    const int T = tile_env;
-#define BENG_CCASE(TT)                                                                                          \
-    if (T == TT) {                                                                                              \
-        const size_t smem = crypto_smem_bytes<TT>();                                                            \
-        auto kern = crypto_kernel<TT, IS_RESET>;                                                                \
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        if (e != cudaSuccess) return (int)e;                                                                    \
-        kern<<<(unsigned)((a.n + TT - 1) / TT), 4 * TT, smem, stream>>>(a);                                     \
-        return finish_launch();                                                                                 \
-    }
-    BENG_CCASE(32) BENG_CCASE(64) BENG_CCASE(128)
-#undef BENG_CCASE
-    return BENG_ERR_UNSUPPORTED;
 }
 
 int check(const beng_crypto_params *p, const beng_crypto_state *st, const beng_crypto_io *io, int64_t n) {
     if (!p || !st || !io || n < 0) return BENG_ERR_BAD_ARG;
     if (!st->scal || !st->meta || !st->ep_return || !st->close || !st->ohlv || !io->obs) return BENG_ERR_BAD_ARG;
-    if (((uintptr_t)io->obs & 15) || ((uintptr_t)st->close & 7)) return BENG_ERR_BAD_ARG;
+    if (((uintptr_t)io->obs & 15) || ((uintptr_t)st->close & 7) || ((uintptr_t)st->ohlv & 15)) return BENG_ERR_BAD_ARG;
     if (p->window_head < 0 || p->window_head >= HIST) return BENG_ERR_BAD_ARG;
     if (p->autoreset_mode < 0 || p->autoreset_mode > 2 || p->action_type < 0 || p->action_type > 1) return BENG_ERR_BAD_ARG;
     if (p->max_steps < 1 || p->max_steps > 65535) return BENG_ERR_UNSUPPORTED;
+    if (n >= (1LL << 26)) return BENG_ERR_UNSUPPORTED;  // 32-bit element offsets in the window addressing (49 * n < 2^32)
     return 0;
 }
 

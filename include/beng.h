@@ -187,10 +187,7 @@ typedef struct beng_crypto_state {
     uint32_t *meta;    /* [2][n]  {step | regime << 16 | flags << 24}, rng_counter */
     double *ep_return; /* [n]     running episode return */
     double *close;     /* [50][n] close prices, ring over slots (see window_head) */
-    float *ohlv;       /* [50][4][n] open, high, low, volume */
-    float *scratch;    /* [12][n] nullable; per-step scratch (11 indicator features + 1/close) used only by the split
-                          step (BENG_CRYPTO_MODE=split): written by its dynamics kernel, consumed by its observation
-                          kernel within the SAME call; no meaning between calls */
+    float *ohlv;       /* [50][n][4] open, high, low, volume: one 16-byte record per (slot, env); 16-byte aligned */
 } beng_crypto_state;
 
 typedef struct beng_crypto_io {
@@ -218,9 +215,9 @@ int beng_crypto_reset(const beng_crypto_params *p, const beng_crypto_state *st, 
 
 /* CryptoTradingEnv.step (:342-398) + _execute_action/_execute_buy/_execute_sell (:400-503) +
  * MarketSimulator.generate_next_price (:132-221) + _get_observation with all TechnicalIndicators (:41-119,
- * :505-561) + auto-reset, for all envs, in ONE kernel launch (the fused two-phase kernel; with BENG_CRYPTO_MODE=split
- * in the environment, two launches: a dynamics/indicator kernel and a streaming observation kernel that hand over
- * through st->scratch).  `actions_dev` is int64[n] or float32[n][2] according to p->action_type. */
+ * :505-561) + auto-reset, for all envs, in ONE kernel launch (persistent CTAs: per-env float64 dynamics, then the
+ * window is streamed once and the indicators are accumulated on the way).  `actions_dev` is int64[n] or
+ * float32[n][2] according to p->action_type.  n_envs must be below 2^26 (BENG_ERR_UNSUPPORTED otherwise). */
 int beng_crypto_step(const beng_crypto_params *p, const beng_crypto_state *st, const void *actions_dev,
                      const beng_crypto_io *io, int64_t n_envs, void *stream);
 

@@ -1,8 +1,8 @@
-"""Import the UNMODIFIED reference modules from /root/reference (build container only).
+"""Import the UNMODIFIED reference modules: from /root/reference in the build container, else from the byte-for-byte
+copies staged under oracle/_ref/ by `python -m oracle.make_ref` (git-ignored; they travel to the GPU box).
 
-TEST INFRASTRUCTURE.  `/root/reference` does not exist on the GPU box; callers must check
-`reference_available()` and skip otherwise.  gymnasium / pygame are not installed in this
-image, so stub packages from oracle/refstubs/ are put on
+TEST INFRASTRUCTURE.  Callers must check `reference_available()` and skip otherwise.  gymnasium / pygame are
+not installed in this image, so stub packages from oracle/refstubs/ are put on
 sys.path for the duration of the import only.
 """
 from __future__ import annotations
@@ -12,8 +12,22 @@ import importlib.util
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("BENG_REFERENCE_ROOT", "/root/reference")
-_STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refstubs")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("BENG_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(root, "snake_env_classic", "snake_env.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
+_STUBS = os.path.join(_HERE, "refstubs")
 _cache = {}
 
 
@@ -34,21 +48,32 @@ def _import_from(path: str, modname: str, extra_sys_path=()):
     if modname in _cache:
         return _cache[modname]
     saved_path = list(sys.path)
+    stub_roots = _stub_names()
     stubbed = {}
     try:
         sys.path[:0] = [_STUBS, *extra_sys_path]
         for n in list(sys.modules):
-            root = n.split(".")[0]
-            if root in ("gymnasium", "pygame", "matplotlib") and root in _stub_names():
-                stubbed[n] = sys.modules.pop(n)
+            if n.split(".")[0] in stub_roots:
+                stubbed[n] = sys.modules.pop(n)  # a real (or earlier stub) module: set aside for the import
         spec = importlib.util.spec_from_file_location(modname, path)
         mod = importlib.util.module_from_spec(spec)
         sys.modules[modname] = mod
         spec.loader.exec_module(mod)
     finally:
         sys.path[:] = saved_path
+        # The reference module keeps its own references to the stubs it imported; sys.modules goes back to what it
+        # was, so a later `import matplotlib` / `import gymnasium` elsewhere in the process never sees a stub.
+        for n in list(sys.modules):
+            if n.split(".")[0] in stub_roots and _is_stub(sys.modules[n]):
+                del sys.modules[n]
+        sys.modules.update(stubbed)
     _cache[modname] = mod
     return mod
+
+
+def _is_stub(mod) -> bool:
+    f = getattr(mod, "__file__", None) or ""
+    return os.path.abspath(f).startswith(_STUBS + os.sep)
 
 
 def load_snake():

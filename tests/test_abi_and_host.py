@@ -50,7 +50,7 @@ def test_argument_errors_do_not_need_a_gpu():
     p = pkg._lib.SnakeParams(20, 1000, 2, 0, 0, 0)
     assert ctypes.sizeof(pkg._lib.CryptoParams) == 96 and ctypes.sizeof(pkg._lib.TrafficParams) == 56
     assert ctypes.sizeof(pkg._lib.BuilderParams) == 24 and ctypes.sizeof(pkg._lib.BuilderIO) == 12 * 8
-    assert ctypes.sizeof(pkg._lib.ClimateParams) == 32 and ctypes.sizeof(pkg._lib.CryptoState) == 48
+    assert ctypes.sizeof(pkg._lib.ClimateParams) == 32 and ctypes.sizeof(pkg._lib.CryptoState) == 40
     st = pkg._lib.SnakeState(None, None)
     io = pkg._lib.SnakeIO()
     assert lib.beng_snake_step(ctypes.byref(p), ctypes.byref(st), None, ctypes.byref(io), 16, None) == -1
