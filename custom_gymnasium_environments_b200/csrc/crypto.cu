@@ -255,16 +255,19 @@ __device__ __forceinline__ double np_sum(F val) {
     return res;
 }
 
-// L2-coherent loads (bypass L1) for data another thread of this CTA may have just rewritten.
-__device__ __forceinline__ double ld_cg_f64(const double *p) {
-    double v;
-    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float4 ld_cg_f32x4(const float4 *p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
+// Streaming (evict-first) loads of the window.  Plain weak loads are enough for data written earlier in the SAME CTA:
+// bar.sync orders the global-memory accesses of the participating threads, and no other CTA touches this env's window.
+__device__ __forceinline__ double ld_win_f64(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_win_f32x4(const float4 *p) { return __ldcs(p); }
+
+// x / 20 correctly rounded without the division subroutine (its slow-path CALL would force every value that is live
+// across it -- the prefetched window of the next unit -- into local memory).  Markstein: with y = RN(1/20),
+// q = RN(x y), r = x - 20 q (exact in an FMA), RN(q + r y) is the correctly rounded quotient for normal-range x.
+__device__ __forceinline__ double div20(double x) {
+    const double y = 0.05;
+    const double q = x * y;
+    const double r = __fma_rn(-20.0, q, x);
+    return __fma_rn(r, y, q);
 }
 
 // _execute_buy, :449-476.  Returns 1 when the order executed.
@@ -420,7 +423,7 @@ __global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
     const uint32_t n32 = (uint32_t)n;
     const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
     const int oldest = head + 1 == HIST ? 0 : head + 1;
-    const float ib_f = (float)a.p.initial_balance;
+    const double inv_ib = 1.0 / a.p.initial_balance;  // (features divide by it; the product differs by <= 1 ulp of float64)
     pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
     pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
 
@@ -635,8 +638,7 @@ __global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
                 }
             }
         }
-        __threadfence();  // this step's candle (and a reset's whole window) must be in L2 before phase 2 reads it
-        __syncthreads();
+        __syncthreads();  // orders this CTA's window writes (the new candle, a reset's whole window) before its reads below
 
         // --------------------------------------------------------------------------------------- phase 2
         const int e = lane, g = wid;
@@ -651,8 +653,8 @@ __global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
 #pragma unroll
                 for (int i = 0; i < C3_PER; ++i) {
                     if (g + C3_G * i < HIST) {
-                        xo[i] = ld_cg_f32x4(obase + soff[i]);  // one 128-bit load: open, high, low, volume
-                        co[i] = ld_cg_f64(cbase + soff[i]);
+                        xo[i] = ld_win_f32x4(obase + soff[i]);  // one 128-bit load: open, high, low, volume
+                        co[i] = ld_win_f64(cbase + soff[i]);
                     }
                 }
             }
@@ -715,12 +717,14 @@ __global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
                         mx = fmaxf(mx, s_mx[q * C3_SUB + e]);
                         mn = fminf(mn, s_mn[q * C3_SUB + e]);
                     }
+                    // (fast float32 quotients, 2 ulp, from here on: the IEEE-rounded ones carry a slow-path CALL, and a
+                    // call inside this loop spills the prefetched window of the next unit)
                     const float range = mx - mn;
                     float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
                     if (range > 0.0f) {
-                        f0 = __fdiv_rn((float)pm, range);
-                        f1 = __fdiv_rn((float)pg, range);
-                        f2 = __fdiv_rn((float)(pm - pg), range);
+                        f0 = __fdividef((float)pm, range);
+                        f1 = __fdividef((float)pg, range);
+                        f2 = __fdividef((float)(pm - pg), range);
                     }
                     dst[254] = f0;
                     dst[255] = f1;
@@ -730,22 +734,24 @@ __global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
                     auto delta = [&](int i) { return wl[(i + 1) * C3_SUB] - wl[i * C3_SUB]; };
                     const double sg = np_sum<14>([&](int i) { const double d = delta(i); return d > 0 ? d : 0.0; });
                     const double sl = np_sum<14>([&](int i) { const double d = delta(i); return d < 0 ? -d : 0.0; });
-                    dst[253] = (sl != 0) ? __fdiv_rn((float)sg, (float)(sg + sl)) : 1.0f;
+                    dst[253] = (sl != 0) ? __fdividef((float)sg, (float)(sg + sl)) : 1.0f;
                 } else if (g == 2) {  // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
                     const double *wl = s_last + e;
-                    const double sma = np_sum<C3_LAST>([&](int i) { return wl[i * C3_SUB]; }) / 20.0;
+                    const double sma = div20(np_sum<C3_LAST>([&](int i) { return wl[i * C3_SUB]; }));  // exact mean
                     const double var = np_sum<C3_LAST>([&](int i) { const double d = wl[i * C3_SUB] - sma; return d * d; });
-                    const double sd = sqrt(var / 20.0);
+                    // std to float32 accuracy (it only scales float32 features): v * rsqrt(v), 0 stays 0
+                    const float var_f = (float)div20(var);
+                    const double sd = (double)(var_f > 0.0f ? var_f * rsqrtf(var_f) : 0.0f);
                     const double upper = sma + (2 * sd), lower = sma - (2 * sd), cur = wl[(C3_LAST - 1) * C3_SUB];
                     const float width = (float)(upper - lower), mid = (float)sma;
-                    dst[257] = (upper > lower) ? __fdiv_rn((float)(cur - lower), width) : 0.5f;
-                    dst[258] = (sma > 0) ? __fdiv_rn(width, mid) : 0.0f;
-                    dst[259] = (sma > 0) ? __fdiv_rn((float)(cur - sma), mid) : 0.0f;
+                    dst[257] = (upper > lower) ? __fdividef((float)(cur - lower), width) : 0.5f;
+                    dst[258] = (sma > 0) ? __fdividef(width, mid) : 0.0f;
+                    dst[259] = (sma > 0) ? __fdividef((float)(cur - sma), mid) : 0.0f;
                 } else if (g == 3) {  // portfolio features :519-527, psychology :559
                     const double cash = s_cash[le], hv = s_hold[le] * s_cur[le];
-                    dst[250] = __fdiv_rn((float)cash, ib_f);
-                    dst[251] = __fdiv_rn((float)hv, ib_f);
-                    dst[252] = __fdiv_rn((float)(cash + hv), ib_f);
+                    dst[250] = (float)(cash * inv_ib);
+                    dst[251] = (float)(hv * inv_ib);
+                    dst[252] = (float)((cash + hv) * inv_ib);
                     dst[260] = s_psych[le];
                 }
             }
@@ -796,6 +802,7 @@ int launch(const CArgs &a, cudaStream_t stream) {
         case 1: return launch3<IS_RESET, 1, false, 3>(a, stream);
         case 2: return launch3<IS_RESET, 2, false, 2>(a, stream);
         case 3: return launch3<IS_RESET, 1, false, 4>(a, stream);
+        case 4: return launch3<IS_RESET, 1, true, 3>(a, stream);
         default: return launch3<IS_RESET, 2, true, 2>(a, stream);
     }
 }
