@@ -88,8 +88,9 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
             self._scal = z(4, n, dt=torch.float64)       # cash, holdings, trend_strength, psychology
             self._meta = z(2, n, dt=torch.int32)         # step | regime<<16 | flags<<24 ; rng counter
             self._ep_return = z(n, dt=torch.float64)
-            self._close = z(HISTORY, n, dt=torch.float64)
-            self._ohlv = z(HISTORY, n, 4, dt=torch.float32)   # open, high, low, volume: one 16-byte record per env
+            pitch = int(self.lib.beng_crypto_window_pitch(n))   # rows padded to whole 32-env units (TMA boxes)
+            self._close = z(HISTORY, pitch, dt=torch.float64)
+            self._ohlv = z(HISTORY, pitch, 4, dt=torch.float32)   # open, high, low, volume: one 16-byte record per env
             # outputs
             self.obs = z(n, OBS_DIM, dt=torch.float32)
             self.reward = z(n, dt=torch.float32)
@@ -148,8 +149,9 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
         """(n, 50, 5) float64 window, oldest first: open, high, low, close, volume (open/high/low/volume are
         kept in float32 on the device)."""
         order = [(self.params.window_head + 1 + k) % HISTORY for k in range(HISTORY)]
-        close = self._close[order]                       # (50, n)
-        ohlv = self._ohlv[order].to(torch.float64)       # (50, n, 4)
+        n = self.num_envs
+        close = self._close[order][:, :n]                # (50, n)
+        ohlv = self._ohlv[order][:, :n].to(torch.float64)  # (50, n, 4)
         cand = torch.stack([ohlv[..., 0], ohlv[..., 1], ohlv[..., 2], close, ohlv[..., 3]], dim=-1)  # (50, n, 5)
         return cand.permute(1, 0, 2).contiguous()
 

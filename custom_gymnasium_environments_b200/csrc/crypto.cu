@@ -24,6 +24,8 @@
 //     stride 261 words = conflict-free) and drained with one bulk asynchronous copy (cp.async.bulk, UBLKCP).
 //
 // HBM-bound: ~2.4 KB per env-step (window read 1.4 KB + observation write 1.04 KB); no tensor-core work.
+#include <cuda.h>
+
 #include <cfloat>
 #include <cstdint>
 #include <cstdio>
@@ -48,6 +50,7 @@ struct CArgs {
     const void *actions;
     const uint8_t *mask;
     long long n;
+    long long pitch;  // row pitch (envs) of the close / ohlv windows: n rounded up to a multiple of 32
     int first_call;
 };
 
@@ -159,13 +162,13 @@ __device__ __noinline__ WarmupResult warmup_window(double *close_arr, float4 *oh
 // its regime check fires (choice 1, trend 2), so candle k starts at ctr + 14 k + 3 * (changes before k).  The lanes start
 // from "no change anywhere", find the first candle whose check fires, shift everything behind it by 3 words, and
 // repeat (one extra pass per regime change: 0.5 on average).
-// `stage` is 100 doubles of warp-private shared memory, element d at stage[(d >> 4) * 128 + (d & 15)].
+// `stage` is 100 doubles of warp-private shared memory, element d at stage[(d >> 4) * stage_stride + (d & 15)].
 // All 32 lanes call this with identical arguments.  Bit-identical to warmup_window() (tests: sparse-reset rollouts).
 __device__ __noinline__ WarmupResult coop_warmup_window(double *close_arr, float4 *ohlv_arr, long long n, long long env,
                                                         int head, beng_crypto_params p, Market m, uint64_t gid,
-                                                        uint32_t ctr, double *stage) {
+                                                        uint32_t ctr, double *stage, int stage_stride) {
     const int lane = threadIdx.x & 31;
-    auto at = [&](int d) -> double & { return stage[(d >> 4) * 128 + (d & 15)]; };
+    auto at = [&](int d) -> double & { return stage[(d >> 4) * stage_stride + (d & 15)]; };
     double volume[2], z[2], vf[2], uh[2], ul[2], uo[2], rt[2] = {0.0, 0.0};
     int pick[2] = {0, 0};
     bool fires[2] = {false, false};
@@ -370,13 +373,14 @@ constexpr MacdWeights make_macd_weights() {
 constexpr MacdWeights k_macd_weights = make_macd_weights();
 __constant__ MacdWeights c_macd = k_macd_weights;
 
-// One env's pre-computed Philox words in shared memory (word j of thread t at w[j * C3_T]); same draw -> value maps as
+// One env's pre-computed Philox words in shared memory (word j of thread t at w[j * NT]); same draw -> value maps as
 // EnvStream (beng_rng.cuh, contract in oracle/philox.py).
+template <int NT>
 struct TableStream {
     const uint32_t *w;
     uint32_t pos, ctr;
     __device__ __forceinline__ uint32_t u32() {
-        const uint32_t v = w[pos * C3_T];
+        const uint32_t v = w[pos * NT];
         ++pos;
         ++ctr;
         return v;
@@ -387,11 +391,209 @@ struct TableStream {
         return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
     }
     __device__ __forceinline__ double uniform(double a, double b) { return a + (b - a) * random53(); }
-    __device__ __forceinline__ double normal(double mu, double sd) {
-        const double u1 = random53(), u2 = random53();
-        return mu + sd * (sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2));
-    }
 };
+
+// Phase 1 of the step kernels: warp `wid` of the CTA steps the 32 envs of unit `u` (lane = env), one thread per env, in
+// the reference's float64 operation order; writes the state, the per-step outputs and this step's candle, rebuilds the
+// windows of envs that reset, and hands (newest close, cash, holdings, psychology, newest open/high/low/volume) to
+// `handover` for phase 2.  `s_rng` is the CTA's [20][NT] table of Philox words.  Returns the warp's reset mask.
+template <bool IS_RESET, int NT, typename Handover>
+__device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, bool unit_ok, int head, uint32_t *s_rng,
+                                                   Handover handover) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long n = a.n, pitch = a.pitch;
+    const long long env = u * C3_SUB + lane;
+    const bool active = unit_ok && env < n;
+    const uint64_t gid = a.p.env_id_base + (uint64_t)env;
+    bool ended = false, need_reset = false;
+    double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
+    double cash = 0.0, holdings = 0.0, ep_ret = 0.0, rew = 0.0, value = 0.0, price_out = 0.0, cur = 1.0;
+    Market m{SIDEWAYS, 0.0, 0.5};
+    int step = 0, term = 0, trade = 0;
+    uint32_t flags = 0, ctr = 0;
+    bool step_at_limit = false;
+    float4 newest = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // open, high, low, volume of this step's candle
+    // ---- (a) state in, one step of the dynamics, termination decision
+    if (active) {
+        // requested together with the state: the old price and the action head the dependency chain
+        double price_pre = 0.0;
+        long long act_pre = 0;
+        float2 actf_pre = make_float2(0.0f, 0.0f);
+        if constexpr (!IS_RESET) {
+            price_pre = a.st.close[(long long)a.p.window_head * pitch + env];
+            if (a.p.action_type == 1) actf_pre = reinterpret_cast<const float2 *>(a.actions)[env];
+            else act_pre = reinterpret_cast<const long long *>(a.actions)[env];
+        }
+        const uint32_t meta = a.st.meta[env];
+        ctr = a.st.meta[n + env];
+        cash = a.st.scal[env];
+        holdings = a.st.scal[n + env];
+        m.trend = a.st.scal[2 * n + env];
+        m.psych = a.st.scal[3 * n + env];
+        step = meta & 0xFFFF;
+        m.regime = (meta >> 16) & 0xFF;
+        flags = meta >> 24;
+        ep_ret = a.st.ep_return[env];
+        if constexpr (IS_RESET) {
+            need_reset = a.mask ? a.mask[env] != 0 : true;
+            if (need_reset && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
+                m.regime = SIDEWAYS;
+                m.trend = 0.0;
+                m.psych = 0.5;
+                ctr = 0;
+            }
+        } else if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
+            need_reset = true;  // the ring head moved by one slot with this call: whole window at the new rotation
+        } else {
+            TableStream<NT> rng{s_rng + tid, ctr & 3u, ctr};
+            {
+                const uint32_t blk0 = ctr >> 2;
+#pragma unroll
+                for (int b = 0; b < C3_RNGW / 4; ++b) {
+                    const Philox4 r = philox4x32_10(blk0 + b, (uint32_t)gid, (uint32_t)(gid >> 32), BENG_STREAM_ENV,
+                                                    (uint32_t)a.p.seed, (uint32_t)(a.p.seed >> 32));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) s_rng[(4 * b + q) * NT + tid] = r.v[q];
+                }
+            }
+            // _execute_action, :400-447
+            const double price = price_pre;
+            const double initial_value = cash + holdings * price;
+            // Order side and size first, then ONE inlined copy of each execution routine, so that lanes of a
+            // warp holding different actions do not walk through separate copies one after the other.
+            int side = 0;  // 1 = buy `amount` of cash, 2 = sell `amount` of crypto
+            double amount = 0.0;
+            if (a.p.action_type == 1) {  // :408-422
+                const float2 act = actf_pre;
+                const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
+                const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
+                if (buy > sell && buy > 0) side = 1, amount = buy;
+                else if (sell > 0) side = 2, amount = sell;
+            } else {  // :424-436; anything outside 1..4 is a hold: the reference does not validate
+                const long long act = act_pre;
+                if (act == 1 || act == 2) side = 1, amount = cash * (act == 1 ? 0.05 : 0.2);
+                else if (act == 3 || act == 4) side = 2, amount = holdings * (act == 3 ? 0.05 : 0.2);
+            }
+            if (side == 1) trade = do_buy(a.p, rng, cash, holdings, amount, price);
+            else if (side == 2) trade = do_sell(a.p, rng, cash, holdings, amount, price);
+            const double final_value = cash + holdings * price;
+            rew = final_value - initial_value;  // valued at the OLD price, :440-441
+            if (!trade) rew -= 1.0;             // :444-445
+            // next candle, :348-365
+            const double volume = rng.uniform(0.5, 2.0);
+            const double new_price = next_price(a.p, m, rng, price, volume);
+            const double high = new_price * rng.uniform(1.0, 1.02);
+            const double low = new_price * rng.uniform(0.98, 1.0);
+            store_candle(a.st.close, reinterpret_cast<float4 *>(a.st.ohlv), pitch, env, head, price, high, low,
+                         new_price, volume);
+            newest = make_float4((float)price, (float)high, (float)low, (float)volume);
+            ctr = rng.ctr;
+            cur = new_price;
+            value = cash + holdings * new_price;
+            price_out = new_price;
+            step = min(step + 1, 65535);
+            step_at_limit = step >= a.p.max_steps;
+            term = step_at_limit || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
+            ep_ret += rew;
+            if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
+                ended = true;
+                st_ret = ep_ret;
+                st_len = (double)step;
+                st_val = value;
+                if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
+                if (a.io.ep_length) a.io.ep_length[env] = step;
+                if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) need_reset = true;
+                else flags |= CFLAG_NEEDS_RESET;
+            }
+        }
+    }
+    // ---- (b) state, hand-over to phase 2 and per-step outputs of every env that does not reset in this call
+    // (done BEFORE the resets so that nothing of the hot path is live across their calls)
+    auto put_state = [&]() {
+        handover(cur, cash, holdings, m.psych, newest);
+        a.st.scal[env] = cash;
+        a.st.scal[n + env] = holdings;
+        a.st.scal[2 * n + env] = m.trend;
+        a.st.scal[3 * n + env] = m.psych;
+        a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
+        a.st.meta[n + env] = ctr;
+        a.st.ep_return[env] = ep_ret;
+    };
+    if (active) {
+        if constexpr (IS_RESET) {
+            if (!need_reset) cur = a.st.close[(long long)head * pitch + env];  // not selected: window unchanged
+        } else {
+            a.io.reward[env] = (float)rew;
+            a.io.terminated[env] = (uint8_t)term;
+            if (a.io.truncated)
+                a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
+            if (a.io.reward64) a.io.reward64[env] = rew;
+            if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
+            if (ended || !need_reset) {  // (a NEXT_STEP reset reports the fresh episode's values below)
+                if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
+                if (a.io.current_price) a.io.current_price[env] = price_out;
+            }
+        }
+        if (!need_reset) put_state();
+    }
+    if constexpr (!IS_RESET) {
+        if (a.io.stats) {
+            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+            if (done_mask) {  // rare: a handful of envs per step
+                const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
+                if (lane == 0) {
+                    atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
+                    atomicAdd(&a.io.stats[1], r);
+                    atomicAdd(&a.io.stats[2], l);
+                    atomicAdd(&a.io.stats[3], v2);
+                }
+            }
+        }
+    }
+    // ---- (c) resets (:301-340).  A few per warp: the whole warp rebuilds each window together (see
+    // coop_warmup_window); many (reset(), or a batch whose episodes all end on the same step): one lane per env.
+    const unsigned reset_mask = __ballot_sync(0xFFFFFFFFu, need_reset);
+    if (reset_mask) {
+        WarmupResult wr{m, ctr, cur};
+        float4 *ohlv4 = reinterpret_cast<float4 *>(a.st.ohlv);
+        if (IS_RESET || __popc(reset_mask) > C3_COOP_MAX) {
+            if (need_reset) wr = warmup_window(a.st.close, ohlv4, pitch, env, head, a.p, m, gid, ctr);
+        } else {
+            __syncwarp();  // every lane is done with its Philox words: their shared-memory rows become the stage
+            double *stage = reinterpret_cast<double *>(s_rng + wid * C3_SUB);
+            for (unsigned rest = reset_mask; rest; rest &= rest - 1) {
+                const int src = __ffs(rest) - 1;
+                Market ms;
+                ms.regime = __shfl_sync(0xFFFFFFFFu, m.regime, src);
+                ms.trend = __shfl_sync(0xFFFFFFFFu, m.trend, src);
+                ms.psych = __shfl_sync(0xFFFFFFFFu, m.psych, src);
+                const uint32_t ctr_s = __shfl_sync(0xFFFFFFFFu, ctr, src);
+                const long long env_s = u * C3_SUB + src;
+                const WarmupResult w1 = coop_warmup_window(a.st.close, ohlv4, pitch, env_s, head, a.p, ms,
+                                                           a.p.env_id_base + (uint64_t)env_s, ctr_s, stage, NT / 2);
+                if (lane == src) wr = w1;
+            }
+        }
+        if (need_reset) {
+            cash = a.p.initial_balance;
+            holdings = 0.0;
+            step = 0;
+            flags = 0;
+            ep_ret = 0.0;
+            m = wr.m;
+            ctr = wr.ctr;
+            cur = wr.last;
+            put_state();
+            if constexpr (!IS_RESET) {
+                if (!ended) {  // NEXT_STEP: this call only delivers the reset observation
+                    if (a.io.portfolio_value) a.io.portfolio_value[env] = cash;
+                    if (a.io.current_price) a.io.current_price[env] = cur;
+                }
+            }
+        }
+    }
+    return reset_mask;
+}
 
 constexpr size_t crypto3_smem_bytes(int nbuf) {
     return (size_t)nbuf * C3_TILE_BYTES + (size_t)C3_T * 8 * 4   // cur, 1/cur, cash, holdings
@@ -420,20 +622,20 @@ __global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long n = a.n;
     const long long n_units = (n + C3_SUB - 1) / C3_SUB;
-    const uint32_t n32 = (uint32_t)n;
+    const uint32_t pitch32 = (uint32_t)a.pitch;
     const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
     const int oldest = head + 1 == HIST ? 0 : head + 1;
     const double inv_ib = 1.0 / a.p.initial_balance;  // (features divide by it; the product differs by <= 1 ulp of float64)
     pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
     pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
 
-    // element offsets (slot * n) of this thread's candles in the [50][n] windows; independent of the unit
-    uint32_t soff[C3_PER];  // 32-bit: check() bounds n below 2^26, so 49 * n < 2^32
+    // element offsets (slot * pitch) of this thread's candles in the [50][pitch] windows; independent of the unit
+    uint32_t soff[C3_PER];  // 32-bit: check() bounds n below 2^26, so 49 * pitch < 2^32
 #pragma unroll
     for (int i = 0; i < C3_PER; ++i) {
         int slot = oldest + wid + C3_G * i;
         slot = slot >= HIST ? slot - HIST : slot;
-        soff[i] = (uint32_t)slot * n32;
+        soff[i] = (uint32_t)slot * pitch32;
     }
 
     uint32_t it = 0;  // sub-tiles drained so far by this CTA (selects the tile buffer)
@@ -445,198 +647,14 @@ __global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
         // --------------------------------------------------------------------------------------- phase 1
         {
             const long long u = (long long)blockIdx.x + (long long)gridDim.x * (j0 + wid);
-            const long long env = u * C3_SUB + lane;
-            const bool active = u < n_units && env < n;
-            const uint64_t gid = a.p.env_id_base + (uint64_t)env;
-            bool ended = false, need_reset = false;
-            double st_ret = 0.0, st_len = 0.0, st_val = 0.0;
-            double cash = 0.0, holdings = 0.0, ep_ret = 0.0, rew = 0.0, value = 0.0, price_out = 0.0, cur = 1.0;
-            Market m{SIDEWAYS, 0.0, 0.5};
-            int step = 0, term = 0, trade = 0;
-            uint32_t flags = 0, ctr = 0;
-            bool step_at_limit = false;
-            // ---- (a) state in, one step of the dynamics, termination decision
-            if (active) {
-                // requested together with the state: the old price and the action head the dependency chain
-                double price_pre = 0.0;
-                long long act_pre = 0;
-                float2 actf_pre = make_float2(0.0f, 0.0f);
-                if constexpr (!IS_RESET) {
-                    price_pre = a.st.close[(long long)a.p.window_head * n + env];
-                    if (a.p.action_type == 1) actf_pre = reinterpret_cast<const float2 *>(a.actions)[env];
-                    else act_pre = reinterpret_cast<const long long *>(a.actions)[env];
-                }
-                const uint32_t meta = a.st.meta[env];
-                ctr = a.st.meta[n + env];
-                cash = a.st.scal[env];
-                holdings = a.st.scal[n + env];
-                m.trend = a.st.scal[2 * n + env];
-                m.psych = a.st.scal[3 * n + env];
-                step = meta & 0xFFFF;
-                m.regime = (meta >> 16) & 0xFF;
-                flags = meta >> 24;
-                ep_ret = a.st.ep_return[env];
-                if constexpr (IS_RESET) {
-                    need_reset = a.mask ? a.mask[env] != 0 : true;
-                    if (need_reset && a.first_call) {  // constructor: MarketSimulator.__init__, :125-130
-                        m.regime = SIDEWAYS;
-                        m.trend = 0.0;
-                        m.psych = 0.5;
-                        ctr = 0;
-                    }
-                } else if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
-                    need_reset = true;  // the ring head moved by one slot with this call: whole window at the new rotation
-                } else {
-                    TableStream rng{s_rng + tid, ctr & 3u, ctr};
-                    {
-                        const uint32_t blk0 = ctr >> 2;
-#pragma unroll
-                        for (int b = 0; b < C3_RNGW / 4; ++b) {
-                            const Philox4 r = philox4x32_10(blk0 + b, (uint32_t)gid, (uint32_t)(gid >> 32), BENG_STREAM_ENV,
-                                                            (uint32_t)a.p.seed, (uint32_t)(a.p.seed >> 32));
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) s_rng[(4 * b + q) * C3_T + tid] = r.v[q];
-                        }
-                    }
-                    // _execute_action, :400-447
-                    const double price = price_pre;
-                    const double initial_value = cash + holdings * price;
-                    // Order side and size first, then ONE inlined copy of each execution routine, so that lanes of a
-                    // warp holding different actions do not walk through separate copies one after the other.
-                    int side = 0;  // 1 = buy `amount` of cash, 2 = sell `amount` of crypto
-                    double amount = 0.0;
-                    if (a.p.action_type == 1) {  // :408-422
-                        const float2 act = actf_pre;
-                        const double buy = clipd((double)act.x, 0.0, 1.0) * (cash * 0.1);
-                        const double sell = clipd((double)act.y, 0.0, 1.0) * (holdings * 0.1);
-                        if (buy > sell && buy > 0) side = 1, amount = buy;
-                        else if (sell > 0) side = 2, amount = sell;
-                    } else {  // :424-436; anything outside 1..4 is a hold: the reference does not validate
-                        const long long act = act_pre;
-                        if (act == 1 || act == 2) side = 1, amount = cash * (act == 1 ? 0.05 : 0.2);
-                        else if (act == 3 || act == 4) side = 2, amount = holdings * (act == 3 ? 0.05 : 0.2);
-                    }
-                    if (side == 1) trade = do_buy(a.p, rng, cash, holdings, amount, price);
-                    else if (side == 2) trade = do_sell(a.p, rng, cash, holdings, amount, price);
-                    const double final_value = cash + holdings * price;
-                    rew = final_value - initial_value;  // valued at the OLD price, :440-441
-                    if (!trade) rew -= 1.0;             // :444-445
-                    // next candle, :348-365
-                    const double volume = rng.uniform(0.5, 2.0);
-                    const double new_price = next_price(a.p, m, rng, price, volume);
-                    const double high = new_price * rng.uniform(1.0, 1.02);
-                    const double low = new_price * rng.uniform(0.98, 1.0);
-                    store_candle(a.st.close, reinterpret_cast<float4 *>(a.st.ohlv), n, env, head, price, high, low,
-                                 new_price, volume);
-                    ctr = rng.ctr;
-                    cur = new_price;
-                    value = cash + holdings * new_price;
-                    price_out = new_price;
-                    step = min(step + 1, 65535);
-                    step_at_limit = step >= a.p.max_steps;
-                    term = step_at_limit || (value <= 0) || (value >= a.p.initial_balance * 10);  // :382-386
-                    ep_ret += rew;
-                    if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
-                        ended = true;
-                        st_ret = ep_ret;
-                        st_len = (double)step;
-                        st_val = value;
-                        if (a.io.ep_return_out) a.io.ep_return_out[env] = ep_ret;
-                        if (a.io.ep_length) a.io.ep_length[env] = step;
-                        if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) need_reset = true;
-                        else flags |= CFLAG_NEEDS_RESET;
-                    }
-                }
-            }
-            // ---- (b) state, hand-over to phase 2 and per-step outputs of every env that does not reset in this call
-            // (done BEFORE the resets so that nothing of the hot path is live across their calls)
-            auto put_state = [&]() {
-                s_cur[tid] = cur;
-                s_invd[tid] = 1.0 / cur;
-                s_cash[tid] = cash;
-                s_hold[tid] = holdings;
-                s_psych[tid] = (float)m.psych;  // :559
-                a.st.scal[env] = cash;
-                a.st.scal[n + env] = holdings;
-                a.st.scal[2 * n + env] = m.trend;
-                a.st.scal[3 * n + env] = m.psych;
-                a.st.meta[env] = (uint32_t)step | ((uint32_t)m.regime << 16) | (flags << 24);
-                a.st.meta[n + env] = ctr;
-                a.st.ep_return[env] = ep_ret;
-            };
-            if (active) {
-                if constexpr (IS_RESET) {
-                    if (!need_reset) cur = a.st.close[(long long)head * n + env];  // not selected: window unchanged
-                } else {
-                    a.io.reward[env] = (float)rew;
-                    a.io.terminated[env] = (uint8_t)term;
-                    if (a.io.truncated)
-                        a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term && step_at_limit);
-                    if (a.io.reward64) a.io.reward64[env] = rew;
-                    if (a.io.trade_kind) a.io.trade_kind[env] = (uint8_t)trade;
-                    if (ended || !need_reset) {  // (a NEXT_STEP reset reports the fresh episode's values below)
-                        if (a.io.portfolio_value) a.io.portfolio_value[env] = value;
-                        if (a.io.current_price) a.io.current_price[env] = price_out;
-                    }
-                }
-                if (!need_reset) put_state();
-            }
-            if constexpr (!IS_RESET) {
-                if (a.io.stats) {
-                    const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
-                    if (done_mask) {  // rare: a handful of envs per step
-                        const double r = warp_sum(st_ret), l = warp_sum(st_len), v2 = warp_sum(st_val);
-                        if (lane == 0) {
-                            atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
-                            atomicAdd(&a.io.stats[1], r);
-                            atomicAdd(&a.io.stats[2], l);
-                            atomicAdd(&a.io.stats[3], v2);
-                        }
-                    }
-                }
-            }
-            // ---- (c) resets (:301-340).  A few per warp: the whole warp rebuilds each window together (see
-            // coop_warmup_window); many (reset(), or a batch whose episodes all end on the same step): one lane per env.
-            const unsigned reset_mask = __ballot_sync(0xFFFFFFFFu, need_reset);
-            if (reset_mask) {
-                WarmupResult wr{m, ctr, cur};
-                float4 *ohlv4 = reinterpret_cast<float4 *>(a.st.ohlv);
-                if (IS_RESET || __popc(reset_mask) > C3_COOP_MAX) {
-                    if (need_reset) wr = warmup_window(a.st.close, ohlv4, n, env, head, a.p, m, gid, ctr);
-                } else {
-                    __syncwarp();  // every lane is done with its Philox words: their shared-memory rows become the stage
-                    double *stage = reinterpret_cast<double *>(s_rng + wid * C3_SUB);
-                    for (unsigned rest = reset_mask; rest; rest &= rest - 1) {
-                        const int src = __ffs(rest) - 1;
-                        Market ms;
-                        ms.regime = __shfl_sync(0xFFFFFFFFu, m.regime, src);
-                        ms.trend = __shfl_sync(0xFFFFFFFFu, m.trend, src);
-                        ms.psych = __shfl_sync(0xFFFFFFFFu, m.psych, src);
-                        const uint32_t ctr_s = __shfl_sync(0xFFFFFFFFu, ctr, src);
-                        const long long env_s = u * C3_SUB + src;
-                        const WarmupResult w1 = coop_warmup_window(a.st.close, ohlv4, n, env_s, head, a.p, ms,
-                                                                   a.p.env_id_base + (uint64_t)env_s, ctr_s, stage);
-                        if (lane == src) wr = w1;
-                    }
-                }
-                if (need_reset) {
-                    cash = a.p.initial_balance;
-                    holdings = 0.0;
-                    step = 0;
-                    flags = 0;
-                    ep_ret = 0.0;
-                    m = wr.m;
-                    ctr = wr.ctr;
-                    cur = wr.last;
-                    put_state();
-                    if constexpr (!IS_RESET) {
-                        if (!ended) {  // NEXT_STEP: this call only delivers the reset observation
-                            if (a.io.portfolio_value) a.io.portfolio_value[env] = cash;
-                            if (a.io.current_price) a.io.current_price[env] = cur;
-                        }
-                    }
-                }
-            }
+            dynamics_phase<IS_RESET, C3_T>(a, u, u < n_units, head, s_rng,
+                                           [&](double cur, double cash, double holdings, double psych, float4) {
+                                               s_cur[tid] = cur;
+                                               s_invd[tid] = 1.0 / cur;
+                                               s_cash[tid] = cash;
+                                               s_hold[tid] = holdings;
+                                               s_psych[tid] = (float)psych;  // :559
+                                           });
         }
         __syncthreads();  // orders this CTA's window writes (the new candle, a reset's whole window) before its reads below
 
@@ -788,6 +806,336 @@ int launch3(const CArgs &a, cudaStream_t stream) {
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------
+// crypto4: the same step with the window brought in by the TMA instead of through registers.
+// crypto3's loop is latency-bound: a CTA can only have ONE unit's window (45 KB) in flight, in registers, and nothing
+// while it runs the dynamics (profiles/crypto_step_r2_ncu_summary.txt: DRAM 42 % busy, 37 % barrier + 20 % scoreboard
+// stalls).  Here ONE 512-thread CTA per SM keeps a ring of three 38.4 KB shared-memory stages filled by
+// cp.async.bulk.tensor (one [50 slots][32 envs] box of the close tensor and one of the open/high/low/volume tensor per
+// unit, completion on an mbarrier): 115 KB per SM are in flight whatever the threads are doing, including across the
+// dynamics phase of the next round.  What a box fetched too early cannot contain is handled explicitly:
+//   * the newest candle (written by the dynamics phase after the box may have been read) comes from shared memory;
+//   * a unit in which some env reset in this call (its whole window was rewritten) is re-read with ordinary loads.
+// Thread (e = lane, g = warp of 16) handles slots k = g, g+16, g+32, g+48; everything else is crypto3's phase 2.
+constexpr int C4_T = 512, C4_G = C4_T / C3_SUB, C4_PER = (HIST + C4_G - 1) / C4_G, C4_STAGES = 3;
+constexpr int C4_STAGE_O = HIST * C3_SUB * 16, C4_STAGE_C = HIST * C3_SUB * 8;  // bytes per stage: 25600 + 12800
+constexpr size_t C4_OFF_STAGE_O = 2 * (size_t)C3_TILE_BYTES;
+constexpr size_t C4_OFF_STAGE_C = C4_OFF_STAGE_O + (size_t)C4_STAGES * C4_STAGE_O;
+constexpr size_t C4_OFF_CUR = C4_OFF_STAGE_C + (size_t)C4_STAGES * C4_STAGE_C;    // double [512]
+constexpr size_t C4_OFF_NEWX = C4_OFF_CUR + (size_t)C4_T * 8;                     // float4 [512]
+constexpr size_t C4_OFF_PORT = C4_OFF_NEWX + (size_t)C4_T * 16;                   // float4 [512]
+constexpr size_t C4_OFF_PM = C4_OFF_PORT + (size_t)C4_T * 16;                     // double [16][32]
+constexpr size_t C4_OFF_PG = C4_OFF_PM + (size_t)C4_T * 8;
+constexpr size_t C4_OFF_LAST = C4_OFF_PG + (size_t)C4_T * 8;                      // double [20][32]
+constexpr size_t C4_OFF_MX = C4_OFF_LAST + (size_t)C3_LAST * C3_SUB * 8;          // float [16][32]
+constexpr size_t C4_OFF_MN = C4_OFF_MX + (size_t)C4_T * 4;
+constexpr size_t C4_OFF_MBAR = C4_OFF_MN + (size_t)C4_T * 4;                      // uint64 [3]
+constexpr size_t C4_OFF_URESET = C4_OFF_MBAR + 32;                                // uint32 [16]
+constexpr size_t C4_SMEM_BYTES = C4_OFF_URESET + C4_G * 4;
+static_assert(C4_SMEM_BYTES <= 227 * 1024, "one CTA per SM: everything has to fit in 227 KB");
+static_assert((size_t)C3_RNGW * C4_T * 4 <= 2 * (size_t)C3_TILE_BYTES, "the Philox table aliases the two tile buffers");
+static_assert(C4_OFF_STAGE_O % 128 == 0 && C4_OFF_STAGE_C % 128 == 0 && C4_STAGE_O % 128 == 0 && C4_STAGE_C % 128 == 0,
+              "TMA destinations are 128-byte aligned");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// One [rows][box_w] box of a 2-D tensor (tensor map in kernel-parameter space) -> shared memory, completion on `bar`.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"((unsigned long long)map), "r"(x), "r"(y), "r"(bar)
+        : "memory");
+}
+
+template <bool IS_RESET>
+__global__ void __launch_bounds__(C4_T, 1) crypto4_kernel(const CArgs a, const __grid_constant__ CUtensorMap tm_close,
+                                                          const __grid_constant__ CUtensorMap tm_ohlv) {
+    constexpr bool USE_TMA = !IS_RESET;  // reset(): every window is rewritten in this launch, nothing to prefetch
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);                               // [2][32][261]
+    uint32_t *s_rng = reinterpret_cast<uint32_t *>(smem_raw);                         // [20][512], phase 1 only
+    const float *st_o = reinterpret_cast<const float *>(smem_raw + C4_OFF_STAGE_O);   // [3][50][32] x float4
+    const double *st_c = reinterpret_cast<const double *>(smem_raw + C4_OFF_STAGE_C); // [3][50][32]
+    double *s_cur = reinterpret_cast<double *>(smem_raw + C4_OFF_CUR);
+    float4 *s_newx = reinterpret_cast<float4 *>(smem_raw + C4_OFF_NEWX);
+    float4 *s_port = reinterpret_cast<float4 *>(smem_raw + C4_OFF_PORT);
+    double *s_pm = reinterpret_cast<double *>(smem_raw + C4_OFF_PM);
+    double *s_pg = reinterpret_cast<double *>(smem_raw + C4_OFF_PG);
+    double *s_last = reinterpret_cast<double *>(smem_raw + C4_OFF_LAST);
+    float *s_mx = reinterpret_cast<float *>(smem_raw + C4_OFF_MX);
+    float *s_mn = reinterpret_cast<float *>(smem_raw + C4_OFF_MN);
+    uint32_t *s_ureset = reinterpret_cast<uint32_t *>(smem_raw + C4_OFF_URESET);
+    const uint32_t mbar0 = smem_u32(smem_raw + C4_OFF_MBAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long n = a.n;
+    const long long n_units = (n + C3_SUB - 1) / C3_SUB;
+    const uint32_t pitch32 = (uint32_t)a.pitch;
+    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
+    const int oldest = head + 1 == HIST ? 0 : head + 1;
+    const double inv_ib = 1.0 / a.p.initial_balance;
+    // units of this CTA: u(q) = blockIdx.x + gridDim.x * q, q = 0 .. total-1
+    const long long total = n_units > blockIdx.x ? (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto unit_of = [&](long long q) { return (long long)blockIdx.x + (long long)gridDim.x * q; };
+
+    int slot_of[C4_PER];  // ring slot of this thread's i-th candle (k = wid + 16 i, oldest first)
+#pragma unroll
+    for (int i = 0; i < C4_PER; ++i) {
+        int slot = oldest + wid + C4_G * i;
+        slot_of[i] = slot >= HIST ? slot - HIST : slot;
+    }
+
+    auto issue_loads = [&](long long q) {  // one thread: both boxes of unit u(q) into stage q % 3
+        const int stage = (int)(q % C4_STAGES);
+        const uint32_t bar = mbar0 + 8u * stage;
+        const int env0 = (int)(unit_of(q) * C3_SUB);
+        mbar_expect_tx(bar, C4_STAGE_O + C4_STAGE_C);
+        tma_load_2d(smem_u32(smem_raw + C4_OFF_STAGE_O + (size_t)stage * C4_STAGE_O), &tm_ohlv, env0 * 4, 0, bar);
+        tma_load_2d(smem_u32(smem_raw + C4_OFF_STAGE_C + (size_t)stage * C4_STAGE_C), &tm_close, env0, 0, bar);
+    };
+
+    if constexpr (USE_TMA) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < C4_STAGES; ++s) mbar_init(mbar0 + 8u * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            fence_proxy_async_smem();
+        }
+    }
+    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
+    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
+    __syncthreads();
+    if constexpr (USE_TMA) {
+        if (tid == 0) {
+            for (long long q = 0; q < C4_STAGES && q < total; ++q) issue_loads(q);
+        }
+    }
+
+#pragma unroll 1
+    for (long long q0 = 0; q0 < total; q0 += C4_G) {
+        // The Philox table of the dynamics phase lives in the tile buffers: the copy engine must have read them.
+        if (tid == 0) bulk_wait_read<0>();
+        __syncthreads();
+
+        // --------------------------------------------------------------------------------------- phase 1
+        {
+            const long long qw = q0 + wid;
+            const unsigned resets = dynamics_phase<IS_RESET, C4_T>(
+                a, unit_of(qw), qw < total, head, s_rng,
+                [&](double cur, double cash, double holdings, double psych, float4 newest) {
+                    const double hv = holdings * cur;  // portfolio features :519-527, psychology :559
+                    s_cur[tid] = cur;
+                    s_newx[tid] = newest;
+                    s_port[tid] = make_float4((float)(cash * inv_ib), (float)(hv * inv_ib), (float)((cash + hv) * inv_ib),
+                                              (float)psych);
+                });
+            if (lane == 0) s_ureset[wid] = resets;
+        }
+        __syncthreads();  // orders this CTA's window writes (the new candle, a reset's whole window) before its reads below
+
+        // --------------------------------------------------------------------------------------- phase 2
+        const int e = lane, g = wid;
+#pragma unroll 1
+        for (int sub = 0; sub < C4_G; ++sub) {
+            const long long q = q0 + sub;
+            if (q >= total) break;  // CTA-uniform
+            const long long sub_first = unit_of(q) * C3_SUB;
+            const long long env = sub_first + e;
+            const int le = sub * C3_SUB + e;  // where phase 1 left this env's values
+            const int stage = (int)(q % C4_STAGES);
+            float *tile = tiles + (q & 1) * (C3_SUB * OBS);
+            float *dst = tile + e * OBS;
+            const bool direct = IS_RESET || s_ureset[sub] != 0;  // CTA-uniform: re-read this unit with ordinary loads
+            if constexpr (USE_TMA) mbar_wait(mbar0 + 8u * stage, (uint32_t)((q / C4_STAGES) & 1));  // (keeps the phases in step)
+
+            if (env < n) {
+                const double cur = s_cur[le];
+                // 1 / cur without the division subroutine: float32 reciprocal + one Newton step in float64 (error ~4e-15)
+                double inv_d = (double)__fdividef(1.0f, (float)cur);
+                inv_d = __fma_rn(inv_d, __fma_rn(-cur, inv_d, 1.0), inv_d);
+                const float inv_f = (float)inv_d;
+                const float4 *so = reinterpret_cast<const float4 *>(st_o + (size_t)stage * (C4_STAGE_O / 4));
+                const double *sc = st_c + (size_t)stage * (C4_STAGE_C / 8);
+                const float4 *go = reinterpret_cast<const float4 *>(a.st.ohlv) + env;
+                const double *gc = a.st.close + env;
+                double pm = 0.0, pg = 0.0;
+                float mx = 0.0f, mn = 0.0f;  // (the newest close itself contributes 0)
+#pragma unroll
+                for (int i = 0; i < C4_PER; ++i) {
+                    const int k = g + C4_G * i;
+                    if (k < HIST) {
+                        float4 x;
+                        double c;
+                        if (direct) {
+                            x = ld_win_f32x4(go + (uint32_t)slot_of[i] * pitch32);
+                            c = ld_win_f64(gc + (uint32_t)slot_of[i] * pitch32);
+                        } else if (k == HIST - 1) {  // this step's candle: the box may have been fetched before it existed
+                            x = s_newx[le];
+                            c = cur;
+                        } else {
+                            x = so[slot_of[i] * C3_SUB + e];
+                            c = sc[slot_of[i] * C3_SUB + e];
+                        }
+                        dst[k * 5 + 0] = x.x * inv_f;  // price_data / current_price, :513-515
+                        dst[k * 5 + 1] = x.y * inv_f;
+                        dst[k * 5 + 2] = x.z * inv_f;
+                        dst[k * 5 + 3] = (float)(c * inv_d);
+                        dst[k * 5 + 4] = x.w * inv_f;
+                        const double d = c - cur;
+                        pm = __fma_rn(c_macd.wm[k], d, pm);
+                        pg = __fma_rn(c_macd.wg[k], d, pg);
+                        const float df = (float)d;
+                        mx = fmaxf(mx, df);
+                        mn = fminf(mn, df);
+                        if (k >= HIST - C3_LAST) s_last[(k - (HIST - C3_LAST)) * C3_SUB + e] = c;
+                    }
+                }
+                s_pm[g * C3_SUB + e] = pm;
+                s_pg[g * C3_SUB + e] = pg;
+                s_mx[g * C3_SUB + e] = mx;
+                s_mn[g * C3_SUB + e] = mn;
+            }
+            __syncthreads();  // the stage has been consumed; partial sums and the last 20 closes are visible
+            if constexpr (USE_TMA) {
+                if (tid == C4_T - 1 && q + C4_STAGES < total) issue_loads(q + C4_STAGES);  // refill the stage just freed
+            }
+            if (env < n) {
+                if (g == 0) {  // MACD(12, 26, 9) normalised by the close range, :538-547
+                    double pm = 0.0, pg = 0.0;
+                    float mx = 0.0f, mn = 0.0f;
+#pragma unroll
+                    for (int qq = 0; qq < C4_G; ++qq) {
+                        pm += s_pm[qq * C3_SUB + e];
+                        pg += s_pg[qq * C3_SUB + e];
+                        mx = fmaxf(mx, s_mx[qq * C3_SUB + e]);
+                        mn = fminf(mn, s_mn[qq * C3_SUB + e]);
+                    }
+                    const float range = mx - mn;
+                    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
+                    if (range > 0.0f) {
+                        f0 = __fdividef((float)pm, range);
+                        f1 = __fdividef((float)pg, range);
+                        f2 = __fdividef((float)(pm - pg), range);
+                    }
+                    dst[254] = f0;
+                    dst[255] = f1;
+                    dst[256] = f2;
+                } else if (g == 1) {  // RSI(14) over the last 14 deltas, :45-61; rsi/100 = gain / (gain + loss)
+                    const double *wl = s_last + 5 * C3_SUB + e;  // the last 15 closes
+                    auto delta = [&](int i) { return wl[(i + 1) * C3_SUB] - wl[i * C3_SUB]; };
+                    const double sg = np_sum<14>([&](int i) { const double d = delta(i); return d > 0 ? d : 0.0; });
+                    const double sl = np_sum<14>([&](int i) { const double d = delta(i); return d < 0 ? -d : 0.0; });
+                    dst[253] = (sl != 0) ? __fdividef((float)sg, (float)(sg + sl)) : 1.0f;
+                } else if (g == 2) {  // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
+                    const double *wl = s_last + e;
+                    const double sma = div20(np_sum<C3_LAST>([&](int i) { return wl[i * C3_SUB]; }));  // exact mean
+                    const double var = np_sum<C3_LAST>([&](int i) { const double d = wl[i * C3_SUB] - sma; return d * d; });
+                    const float var_f = (float)div20(var);
+                    const double sd = (double)(var_f > 0.0f ? var_f * rsqrtf(var_f) : 0.0f);
+                    const double upper = sma + (2 * sd), lower = sma - (2 * sd), cur = wl[(C3_LAST - 1) * C3_SUB];
+                    const float width = (float)(upper - lower), mid = (float)sma;
+                    dst[257] = (upper > lower) ? __fdividef((float)(cur - lower), width) : 0.5f;
+                    dst[258] = (sma > 0) ? __fdividef(width, mid) : 0.0f;
+                    dst[259] = (sma > 0) ? __fdividef((float)(cur - sma), mid) : 0.0f;
+                } else if (g == 3) {
+                    const float4 pf = s_port[le];
+                    dst[250] = pf.x;
+                    dst[251] = pf.y;
+                    dst[252] = pf.z;
+                    dst[260] = pf.w;
+                }
+            }
+            fence_proxy_async_smem();
+            if (tid == 0) bulk_wait_read<0>();  // the copy issued one unit ago has read the other tile buffer
+            __syncthreads();
+            if (tid == 0) {
+                const long long n_here = min((long long)C3_SUB, n - sub_first);
+                const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
+                const uint32_t bulk = bytes & ~15u;
+                if (bulk) bulk_store_s2g(a.io.obs + sub_first * OBS, tile, bulk);
+                bulk_commit();
+                for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[sub_first * OBS + i] = tile[i];  // ragged tail
+            }
+        }
+    }
+    if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the copy engine's reads
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libbeng does not link libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// [50][pitch * elems_per_env] tensor of `type`, box = all 50 slots x one 32-env unit.
+int make_window_map(CUtensorMap *map, void *base, long long pitch, CUtensorMapDataType type, int elem_bytes,
+                    int elems_per_env) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return BENG_ERR_UNSUPPORTED;
+    const cuuint64_t dims[2] = {(cuuint64_t)pitch * elems_per_env, (cuuint64_t)HIST};
+    const cuuint64_t strides[1] = {(cuuint64_t)pitch * elems_per_env * elem_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)(C3_SUB * elems_per_env), (cuuint32_t)HIST};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, type, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : BENG_ERR_BAD_ARG;
+}
+
+template <bool IS_RESET>
+int launch4(const CArgs &a, cudaStream_t stream) {
+    CUtensorMap tm_close, tm_ohlv;
+    if (int rc = make_window_map(&tm_close, a.st.close, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, 1)) return rc;
+    if (int rc = make_window_map(&tm_ohlv, a.st.ohlv, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 4)) return rc;
+    auto kern = crypto4_kernel<IS_RESET>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C4_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    const long long n_units = (a.n + C3_SUB - 1) / C3_SUB;
+    long long grid = device_sm_count();
+    if (grid > n_units) grid = n_units;
+    static const bool use_pdl = getenv("BENG_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(C4_T);
+    cfg.dynamicSmemBytes = C4_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, a, tm_close, tm_ohlv);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)e;
+}
+
 template <bool IS_RESET>
 int launch(const CArgs &a, cudaStream_t stream) {
     // BENG_CRYPTO_VARIANT (read once): 0 = crypto3 two tile buffers + register prefetch, 2 CTAs/SM (default);
@@ -803,6 +1151,7 @@ int launch(const CArgs &a, cudaStream_t stream) {
         case 2: return launch3<IS_RESET, 2, false, 2>(a, stream);
         case 3: return launch3<IS_RESET, 1, false, 4>(a, stream);
         case 4: return launch3<IS_RESET, 1, true, 3>(a, stream);
+        case 7: return launch4<IS_RESET>(a, stream);
         default: return launch3<IS_RESET, 2, true, 2>(a, stream);
     }
 }
@@ -823,11 +1172,13 @@ int check(const beng_crypto_params *p, const beng_crypto_state *st, const beng_c
 
 extern "C" {
 
+int64_t beng_crypto_window_pitch(int64_t n_envs) { return (n_envs + 31) & ~(int64_t)31; }
+
 int beng_crypto_reset(const beng_crypto_params *p, const beng_crypto_state *st, const beng_crypto_io *io,
                       const uint8_t *mask_dev, int64_t n_envs, int32_t first_call, void *stream) {
     if (int rc = beng::check(p, st, io, n_envs)) return rc;
     if (n_envs == 0) return 0;
-    beng::CArgs a{*p, *st, *io, nullptr, mask_dev, (long long)n_envs, first_call};
+    beng::CArgs a{*p, *st, *io, nullptr, mask_dev, (long long)n_envs, beng_crypto_window_pitch(n_envs), first_call};
     return beng::launch<true>(a, (cudaStream_t)stream);
 }
 
@@ -836,7 +1187,7 @@ int beng_crypto_step(const beng_crypto_params *p, const beng_crypto_state *st, c
     if (int rc = beng::check(p, st, io, n_envs)) return rc;
     if (!actions_dev || !io->reward || !io->terminated) return BENG_ERR_BAD_ARG;
     if (n_envs == 0) return 0;
-    beng::CArgs a{*p, *st, *io, actions_dev, nullptr, (long long)n_envs, 0};
+    beng::CArgs a{*p, *st, *io, actions_dev, nullptr, (long long)n_envs, beng_crypto_window_pitch(n_envs), 0};
     return beng::launch<false>(a, (cudaStream_t)stream);
 }
 

@@ -186,8 +186,10 @@ typedef struct beng_crypto_state {
     double *scal;      /* [4][n]  cash, holdings, trend_strength, market_psychology */
     uint32_t *meta;    /* [2][n]  {step | regime << 16 | flags << 24}, rng_counter */
     double *ep_return; /* [n]     running episode return */
-    double *close;     /* [50][n] close prices, ring over slots (see window_head) */
-    float *ohlv;       /* [50][n][4] open, high, low, volume: one 16-byte record per (slot, env); 16-byte aligned */
+    double *close;     /* [50][pitch] close prices, ring over slots (see window_head); pitch =
+                          beng_crypto_window_pitch(n) = n rounded up to a multiple of 32, so that every 32-env unit of
+                          every slot is one aligned box for the tensor-map (TMA) loads; 128-byte aligned */
+    float *ohlv;       /* [50][pitch][4] open, high, low, volume: one 16-byte record per (slot, env); 128-byte aligned */
 } beng_crypto_state;
 
 typedef struct beng_crypto_io {
@@ -205,6 +207,9 @@ typedef struct beng_crypto_io {
     int32_t *ep_length;      /* [n] */
     double *stats;           /* [4] running {n_episodes, sum_return, sum_length, sum_final_value}; nullable */
 } beng_crypto_io;
+
+/* Row pitch (in envs) of beng_crypto_state.close / .ohlv for a batch of n_envs. */
+int64_t beng_crypto_window_pitch(int64_t n_envs);
 
 /* CryptoTradingEnv.reset (:301-340) for envs with mask[i] != 0 (NULL = all): 50 warm-up candles from 50000.0,
  * cash/holdings/step reset, the MarketSimulator state is NOT reset.  first_call != 0 is the
