@@ -308,36 +308,52 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// crypto3 (the default): persistent 256-thread CTAs over 32-env UNITS (unit u = envs [32u, 32u+32)), eight units per
-// round, units strided over the grid (unit = blockIdx + gridDim * j) so that every CTA gets the same number +-1.
+// The step kernels.  Work unit: 32 consecutive envs (unit u = envs [32u, 32u+32)); units are strided over the grid
+// (u(q) = blockIdx + gridDim * q), so every persistent CTA gets the same number +-1.
 //
-//   phase 1  warp w owns unit j0+w, one lane per env: ONLY the dynamics (trade, Philox draws, Box-Muller price step,
-//            candle, termination, auto-reset) in the reference's float64 operation order.  The step's Philox words are
-//            computed up front -- five blocks, no data-dependent branch -- and parked in shared memory, so a draw is one
-//            LDS at a running index instead of a divergent "is my block cached?" branch per draw.
-//   phase 2  for each of the round's units all eight warps stream its window: thread (e = lane, g = warp) fetches slots
-//            k = g, g+8, ... of env e (35 coalesced L2-coherent loads), normalises them into the 33 KB observation tile
-//            AND accumulates its share of the indicator work:
+// Per unit there are two stages:
+//   DYNAMICS (dynamics_phase, one warp, lane = env): ONLY what feeds back into the state -- trade, Philox draws,
+//            Box-Muller price step, candle, termination, auto-reset -- in the reference's float64 operation order.
+//   OBSERVATION (compose_unit + finish_unit, 16 warps): the unit's window is streamed ONCE.  Thread (e = lane, g = warp)
+//            takes slots k = g, g+16, g+32, g+48 of env e, normalises them into the 32 x 261 float tile and accumulates
+//            its share of the indicator work on the way:
 //              * MACD line, signal line: an EMA seeded with prices[0] is a LINEAR function of the window, and so is the
 //                reference's EMA-of-MACD-history (:94-100); both are dot products of the 50 closes with constant weight
 //                vectors (c_macd, built at compile time by running the reference's recurrences on unit vectors).  The
 //                weights sum to zero, so the products are taken with (close - newest close), which is exact (Sterbenz)
-//                and keeps the partial sums small.  Thread (e, g) adds its 7 terms; the 8 partials meet in shared memory.
+//                and keeps the partial sums small.  The 16 partials per env meet in shared memory.
 //              * max/min of the closes for the MACD normalisation: float32 max/min of (close - newest close); the range
 //                is only a divisor of an observation feature (relative error 1.2e-7 against the allowed 1e-5).
 //              * the last 20 closes (Bollinger window; its last 15 give the RSI deltas) are dropped into shared memory.
-//            After one barrier, warps 0..3 finish MACD / RSI / Bollinger / portfolio features for the 32 envs (sums in
-//            float64 and NumPy's pairwise order; the final quotients, which only feed float32 features, in float32),
-//            then one thread drains the tile with a bulk asynchronous copy.
+//            After one barrier, warps 0..3 finish MACD / RSI / Bollinger / portfolio features for the 32 envs with short
+//            tree-shaped float64 sums and fast float32 quotients (nothing in this loop may CALL: a call spills whatever
+//            is live across it), then one thread drains the tile with a bulk asynchronous copy (UBLKCP).
 // What keeps the reference's exact float64 operation order: everything that feeds back into the state (cash, holdings,
-// price walk, psychology, reward).  What does not: the 11 indicator features, which are float32 outputs checked at
-// rtol 1e-5 / atol 1e-6 (tests/test_crypto_gpu.py); their error against the oracle is ~1e-7.
-constexpr int C3_T = 256, C3_SUB = 32, C3_G = C3_T / C3_SUB, C3_PER = (HIST + C3_G - 1) / C3_G;
-constexpr int C3_RNGW = 20;   // Philox words per env-step: <= 3 (block offset) + 2 (slippage) + 2 + 2 + 3 + 4 + 2 + 2
-constexpr int C3_LAST = 20;   // closes kept for Bollinger / RSI
+// price walk, psychology, reward).  What does not: the 11 indicator features, float32 outputs checked at rtol 1e-5 /
+// atol 1e-6 (tests/test_crypto_gpu.py); their error against the oracle is ~1e-7.
+//
+// The window comes in through the TMA: a ring of three 38.4 KB shared-memory stages filled by cp.async.bulk.tensor (one
+// [50 slots][32 envs] box of the close tensor and one of the open/high/low/volume tensor per unit, completion on an
+// mbarrier), so 115 KB per SM are in flight whatever the threads are doing.  What a box fetched early cannot contain is
+// handled explicitly: the newest candle (written by the dynamics after the box may have been read) comes from shared
+// memory, and a unit in which some env reset in this call (its whole window was rewritten) is re-read with ordinary loads.
+//
+// Two kernels share these stages:
+//   crypto5_kernel (the step)  warp-specialised, 768 threads, one CTA per SM: 16 OBSERVATION warps (64 registers after
+//       setmaxnreg.dec) and 8 DYNAMICS warps (112 registers after setmaxnreg.inc) that run up to 8 units ahead; a
+//       dynamics warp hands its unit over through its slot of an 8-deep shared-memory ring (mbarriers ready[]/freed[]).
+//       The ~13,000-cycle dependency chain of a unit's dynamics therefore never sits on the observation path
+//       (in the bulk-synchronous kernel it was 29 % of the step, profiles/crypto_step_r2_ncu_summary.txt).
+//   crypto4_kernel (reset(), and BENG_CRYPTO_VARIANT=4 for A/B)  bulk-synchronous, 512 threads: rounds of 16 units,
+//       all warps run the dynamics of the round, then the observation stage of its units one after the other.
+constexpr int C3_SUB = 32;      // envs per unit
+constexpr int C3_RNGW = 20;     // Philox words per env-step: <= 3 (block offset) + 2 (slippage) + 2 + 2 + 3 + 4 + 2 + 2
+constexpr int C3_LAST = 20;     // closes kept for Bollinger / RSI
 constexpr int C3_COOP_MAX = 8;  // resets per warp up to which each one is rebuilt by the whole warp
 constexpr int C3_TILE_BYTES = C3_SUB * OBS * (int)sizeof(float);
 static_assert(C3_TILE_BYTES % 128 == 0, "tile buffers stay 128-byte aligned");
+constexpr int OBS_WARPS = 16, OBS_T = OBS_WARPS * 32, OBS_PER = (HIST + OBS_WARPS - 1) / OBS_WARPS, TMA_STAGES = 3;
+constexpr int STAGE_O = HIST * C3_SUB * 16, STAGE_C = HIST * C3_SUB * 8;  // bytes per stage: 25600 + 12800
 
 struct MacdWeights {
     double wm[HIST];  // MACD line   = sum_k wm[k] * close[k]   (k = 0 oldest)
@@ -393,14 +409,18 @@ struct TableStream {
     __device__ __forceinline__ double uniform(double a, double b) { return a + (b - a) * random53(); }
 };
 
-// Phase 1 of the step kernels: warp `wid` of the CTA steps the 32 envs of unit `u` (lane = env), one thread per env, in
-// the reference's float64 operation order; writes the state, the per-step outputs and this step's candle, rebuilds the
-// windows of envs that reset, and hands (newest close, cash, holdings, psychology, newest open/high/low/volume) to
-// `handover` for phase 2.  `s_rng` is the CTA's [20][NT] table of Philox words.  Returns the warp's reset mask.
+// The dynamics of one 32-env unit `u`, run by ONE warp (lane = env), one thread per env, in the reference's float64
+// operation order: trade, Philox draws, Box-Muller price step, candle, termination, auto-reset.  Writes the state, the
+// per-step outputs and this step's candle, rebuilds the windows of envs that reset, and hands (newest close, cash,
+// holdings, psychology, newest open/high/low/volume) to `handover` for the observation stage.
+// The step's Philox words are computed up front -- five blocks, no data-dependent branch -- and parked in shared memory
+// (`tbl` = this thread's column of a [20][NT] table), so a draw is one LDS at a running index instead of a divergent
+// "is my block cached?" branch per draw.  `coop_stage` (100 doubles, element d at (d >> 4) * coop_stride + (d & 15),
+// warp-private, may alias the warp's table rows) is the scratch of coop_warmup_window.  Returns the warp's reset mask.
 template <bool IS_RESET, int NT, typename Handover>
-__device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, bool unit_ok, int head, uint32_t *s_rng,
-                                                   Handover handover) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+__device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, bool unit_ok, int head, uint32_t *tbl,
+                                                   double *coop_stage, int coop_stride, Handover handover) {
+    const int lane = threadIdx.x & 31;
     const long long n = a.n, pitch = a.pitch;
     const long long env = u * C3_SUB + lane;
     const bool active = unit_ok && env < n;
@@ -445,7 +465,7 @@ __device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, 
         } else if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & CFLAG_NEEDS_RESET)) {
             need_reset = true;  // the ring head moved by one slot with this call: whole window at the new rotation
         } else {
-            TableStream<NT> rng{s_rng + tid, ctr & 3u, ctr};
+            TableStream<NT> rng{tbl, ctr & 3u, ctr};
             {
                 const uint32_t blk0 = ctr >> 2;
 #pragma unroll
@@ -453,7 +473,7 @@ __device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, 
                     const Philox4 r = philox4x32_10(blk0 + b, (uint32_t)gid, (uint32_t)(gid >> 32), BENG_STREAM_ENV,
                                                     (uint32_t)a.p.seed, (uint32_t)(a.p.seed >> 32));
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) s_rng[(4 * b + q) * NT + tid] = r.v[q];
+                    for (int q = 0; q < 4; ++q) tbl[(4 * b + q) * NT] = r.v[q];
                 }
             }
             // _execute_action, :400-447
@@ -560,7 +580,6 @@ __device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, 
             if (need_reset) wr = warmup_window(a.st.close, ohlv4, pitch, env, head, a.p, m, gid, ctr);
         } else {
             __syncwarp();  // every lane is done with its Philox words: their shared-memory rows become the stage
-            double *stage = reinterpret_cast<double *>(s_rng + wid * C3_SUB);
             for (unsigned rest = reset_mask; rest; rest &= rest - 1) {
                 const int src = __ffs(rest) - 1;
                 Market ms;
@@ -570,7 +589,7 @@ __device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, 
                 const uint32_t ctr_s = __shfl_sync(0xFFFFFFFFu, ctr, src);
                 const long long env_s = u * C3_SUB + src;
                 const WarmupResult w1 = coop_warmup_window(a.st.close, ohlv4, pitch, env_s, head, a.p, ms,
-                                                           a.p.env_id_base + (uint64_t)env_s, ctr_s, stage, NT / 2);
+                                                           a.p.env_id_base + (uint64_t)env_s, ctr_s, coop_stage, coop_stride);
                 if (lane == src) wr = w1;
             }
         }
@@ -595,251 +614,13 @@ __device__ __forceinline__ unsigned dynamics_phase(const CArgs &a, long long u, 
     return reset_mask;
 }
 
-constexpr size_t crypto3_smem_bytes(int nbuf) {
-    return (size_t)nbuf * C3_TILE_BYTES + (size_t)C3_T * 8 * 4   // cur, 1/cur, cash, holdings
-           + (size_t)C3_T * 8 * 2                                // MACD / signal partials [8][32]
-           + (size_t)C3_LAST * C3_SUB * 8                        // last 20 closes [20][32]
-           + (size_t)C3_T * 4 * 3                                // psychology, max / min partials
-           + (size_t)C3_RNGW * C3_T * 4;                         // Philox words [20][256]
-}
-
-template <bool IS_RESET, int NBUF, bool PREFETCH, int MINB>
-__global__ void __launch_bounds__(C3_T, MINB) crypto3_kernel(const CArgs a) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);                                   // [NBUF][32][261]
-    double *s_cur = reinterpret_cast<double *>(smem_raw + (size_t)NBUF * C3_TILE_BYTES);  // [256] newest close
-    double *s_invd = s_cur + C3_T;                                                        // [256] 1 / newest close
-    double *s_cash = s_invd + C3_T;
-    double *s_hold = s_cash + C3_T;
-    double *s_pm = s_hold + C3_T;                      // [8][32] MACD-line partials
-    double *s_pg = s_pm + C3_T;                        // [8][32] signal-line partials
-    double *s_last = s_pg + C3_T;                      // [20][32]
-    float *s_psych = reinterpret_cast<float *>(s_last + C3_LAST * C3_SUB);
-    float *s_mx = s_psych + C3_T;                      // [8][32]
-    float *s_mn = s_mx + C3_T;
-    uint32_t *s_rng = reinterpret_cast<uint32_t *>(s_mn + C3_T);  // [20][256]
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long n = a.n;
-    const long long n_units = (n + C3_SUB - 1) / C3_SUB;
-    const uint32_t pitch32 = (uint32_t)a.pitch;
-    const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
-    const int oldest = head + 1 == HIST ? 0 : head + 1;
-    const double inv_ib = 1.0 / a.p.initial_balance;  // (features divide by it; the product differs by <= 1 ulp of float64)
-    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
-    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
-
-    // element offsets (slot * pitch) of this thread's candles in the [50][pitch] windows; independent of the unit
-    uint32_t soff[C3_PER];  // 32-bit: check() bounds n below 2^26, so 49 * pitch < 2^32
-#pragma unroll
-    for (int i = 0; i < C3_PER; ++i) {
-        int slot = oldest + wid + C3_G * i;
-        slot = slot >= HIST ? slot - HIST : slot;
-        soff[i] = (uint32_t)slot * pitch32;
-    }
-
-    uint32_t it = 0;  // sub-tiles drained so far by this CTA (selects the tile buffer)
-#pragma unroll 1
-    for (long long j0 = 0;; j0 += C3_G) {
-        const long long u_first = (long long)blockIdx.x + (long long)gridDim.x * j0;
-        if (u_first >= n_units) break;  // CTA-uniform
-
-        // --------------------------------------------------------------------------------------- phase 1
-        {
-            const long long u = (long long)blockIdx.x + (long long)gridDim.x * (j0 + wid);
-            dynamics_phase<IS_RESET, C3_T>(a, u, u < n_units, head, s_rng,
-                                           [&](double cur, double cash, double holdings, double psych, float4) {
-                                               s_cur[tid] = cur;
-                                               s_invd[tid] = 1.0 / cur;
-                                               s_cash[tid] = cash;
-                                               s_hold[tid] = holdings;
-                                               s_psych[tid] = (float)psych;  // :559
-                                           });
-        }
-        __syncthreads();  // orders this CTA's window writes (the new candle, a reset's whole window) before its reads below
-
-        // --------------------------------------------------------------------------------------- phase 2
-        const int e = lane, g = wid;
-        float4 x[C3_PER];
-        double c[C3_PER];
-        auto fetch = [&](int sub, float4 (&xo)[C3_PER], double (&co)[C3_PER]) {
-            const long long u = (long long)blockIdx.x + (long long)gridDim.x * (j0 + sub);
-            const long long env = u * C3_SUB + e;
-            if (sub < C3_G && u < n_units && env < n) {
-                const float4 *obase = reinterpret_cast<const float4 *>(a.st.ohlv) + env;
-                const double *cbase = a.st.close + env;
-#pragma unroll
-                for (int i = 0; i < C3_PER; ++i) {
-                    if (g + C3_G * i < HIST) {
-                        xo[i] = ld_win_f32x4(obase + soff[i]);  // one 128-bit load: open, high, low, volume
-                        co[i] = ld_win_f64(cbase + soff[i]);
-                    }
-                }
-            }
-        };
-        if constexpr (PREFETCH) fetch(0, x, c);
-#pragma unroll 1
-        for (int sub = 0; sub < C3_G; ++sub, ++it) {
-            const long long u = (long long)blockIdx.x + (long long)gridDim.x * (j0 + sub);
-            if (u >= n_units) break;  // CTA-uniform
-            const long long sub_first = u * C3_SUB;
-            const long long env = sub_first + e;
-            const int le = sub * C3_SUB + e;  // where phase 1 left this env's values
-            float *tile = tiles + (NBUF == 2 ? (it & 1u) : 0u) * (C3_SUB * OBS);
-            if constexpr (!PREFETCH) fetch(sub, x, c);
-            if constexpr (NBUF == 1) {
-                if (it > 0) {  // the previous bulk copy must have read the (single) tile buffer
-                    if (tid == 0) bulk_wait_read<0>();
-                    __syncthreads();
-                }
-            }
-            float *dst = tile + e * OBS;
-            if (env < n) {
-                const double cur = s_cur[le], inv_d = s_invd[le];
-                const float inv_f = (float)inv_d;
-                double pm = 0.0, pg = 0.0;
-                float mx = 0.0f, mn = 0.0f;  // (the newest close itself contributes 0)
-#pragma unroll
-                for (int i = 0; i < C3_PER; ++i) {
-                    const int k = g + C3_G * i;
-                    if (k < HIST) {
-                        dst[k * 5 + 0] = x[i].x * inv_f;  // price_data / current_price, :513-515
-                        dst[k * 5 + 1] = x[i].y * inv_f;
-                        dst[k * 5 + 2] = x[i].z * inv_f;
-                        dst[k * 5 + 3] = (float)(c[i] * inv_d);
-                        dst[k * 5 + 4] = x[i].w * inv_f;
-                        const double d = c[i] - cur;
-                        pm = __fma_rn(c_macd.wm[k], d, pm);
-                        pg = __fma_rn(c_macd.wg[k], d, pg);
-                        const float df = (float)d;
-                        mx = fmaxf(mx, df);
-                        mn = fminf(mn, df);
-                        if (k >= HIST - C3_LAST) s_last[(k - (HIST - C3_LAST)) * C3_SUB + e] = c[i];
-                    }
-                }
-                s_pm[g * C3_SUB + e] = pm;
-                s_pg[g * C3_SUB + e] = pg;
-                s_mx[g * C3_SUB + e] = mx;
-                s_mn[g * C3_SUB + e] = mn;
-            }
-            if constexpr (PREFETCH) fetch(sub + 1, x, c);  // next unit's loads go out before the hand-over below
-            __syncthreads();
-            if (env < n) {
-                if (g == 0) {  // MACD(12, 26, 9) normalised by the close range, :538-547
-                    double pm = 0.0, pg = 0.0;
-                    float mx = 0.0f, mn = 0.0f;
-#pragma unroll
-                    for (int q = 0; q < C3_G; ++q) {
-                        pm += s_pm[q * C3_SUB + e];
-                        pg += s_pg[q * C3_SUB + e];
-                        mx = fmaxf(mx, s_mx[q * C3_SUB + e]);
-                        mn = fminf(mn, s_mn[q * C3_SUB + e]);
-                    }
-                    // (fast float32 quotients, 2 ulp, from here on: the IEEE-rounded ones carry a slow-path CALL, and a
-                    // call inside this loop spills the prefetched window of the next unit)
-                    const float range = mx - mn;
-                    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
-                    if (range > 0.0f) {
-                        f0 = __fdividef((float)pm, range);
-                        f1 = __fdividef((float)pg, range);
-                        f2 = __fdividef((float)(pm - pg), range);
-                    }
-                    dst[254] = f0;
-                    dst[255] = f1;
-                    dst[256] = f2;
-                } else if (g == 1) {  // RSI(14) over the last 14 deltas, :45-61; rsi/100 = gain / (gain + loss)
-                    const double *wl = s_last + 5 * C3_SUB + e;  // the last 15 closes
-                    auto delta = [&](int i) { return wl[(i + 1) * C3_SUB] - wl[i * C3_SUB]; };
-                    const double sg = np_sum<14>([&](int i) { const double d = delta(i); return d > 0 ? d : 0.0; });
-                    const double sl = np_sum<14>([&](int i) { const double d = delta(i); return d < 0 ? -d : 0.0; });
-                    dst[253] = (sl != 0) ? __fdividef((float)sg, (float)(sg + sl)) : 1.0f;
-                } else if (g == 2) {  // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
-                    const double *wl = s_last + e;
-                    const double sma = div20(np_sum<C3_LAST>([&](int i) { return wl[i * C3_SUB]; }));  // exact mean
-                    const double var = np_sum<C3_LAST>([&](int i) { const double d = wl[i * C3_SUB] - sma; return d * d; });
-                    // std to float32 accuracy (it only scales float32 features): v * rsqrt(v), 0 stays 0
-                    const float var_f = (float)div20(var);
-                    const double sd = (double)(var_f > 0.0f ? var_f * rsqrtf(var_f) : 0.0f);
-                    const double upper = sma + (2 * sd), lower = sma - (2 * sd), cur = wl[(C3_LAST - 1) * C3_SUB];
-                    const float width = (float)(upper - lower), mid = (float)sma;
-                    dst[257] = (upper > lower) ? __fdividef((float)(cur - lower), width) : 0.5f;
-                    dst[258] = (sma > 0) ? __fdividef(width, mid) : 0.0f;
-                    dst[259] = (sma > 0) ? __fdividef((float)(cur - sma), mid) : 0.0f;
-                } else if (g == 3) {  // portfolio features :519-527, psychology :559
-                    const double cash = s_cash[le], hv = s_hold[le] * s_cur[le];
-                    dst[250] = (float)(cash * inv_ib);
-                    dst[251] = (float)(hv * inv_ib);
-                    dst[252] = (float)((cash + hv) * inv_ib);
-                    dst[260] = s_psych[le];
-                }
-            }
-            fence_proxy_async_smem();
-            if constexpr (NBUF == 2) {
-                if (tid == 0) bulk_wait_read<0>();  // the copy issued one sub-tile ago has read the other buffer
-            }
-            __syncthreads();
-            if (tid == 0) {
-                const long long n_here = min((long long)C3_SUB, n - sub_first);
-                const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
-                const uint32_t bulk = bytes & ~15u;
-                if (bulk) bulk_store_s2g(a.io.obs + sub_first * OBS, tile, bulk);
-                bulk_commit();
-                for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[sub_first * OBS + i] = tile[i];  // ragged tail
-            }
-        }
-    }
-    if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the copy engine's reads
-}
-
-template <bool IS_RESET, int NBUF, bool PREFETCH, int MINB>
-int launch3(const CArgs &a, cudaStream_t stream) {
-    const size_t smem = crypto3_smem_bytes(NBUF);
-    auto kern = crypto3_kernel<IS_RESET, NBUF, PREFETCH, MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const long long n_units = (a.n + C3_SUB - 1) / C3_SUB;
-    long long grid = (long long)MINB * device_sm_count();
-    if (grid > n_units) grid = n_units;
-    e = launch_pdl(kern, dim3((unsigned)grid), dim3(C3_T), smem, stream, a);
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    return (int)e;
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------
-// crypto4: the same step with the window brought in by the TMA instead of through registers.
-// crypto3's loop is latency-bound: a CTA can only have ONE unit's window (45 KB) in flight, in registers, and nothing
-// while it runs the dynamics (profiles/crypto_step_r2_ncu_summary.txt: DRAM 42 % busy, 37 % barrier + 20 % scoreboard
-// stalls).  Here ONE 512-thread CTA per SM keeps a ring of three 38.4 KB shared-memory stages filled by
-// cp.async.bulk.tensor (one [50 slots][32 envs] box of the close tensor and one of the open/high/low/volume tensor per
-// unit, completion on an mbarrier): 115 KB per SM are in flight whatever the threads are doing, including across the
-// dynamics phase of the next round.  What a box fetched too early cannot contain is handled explicitly:
-//   * the newest candle (written by the dynamics phase after the box may have been read) comes from shared memory;
-//   * a unit in which some env reset in this call (its whole window was rewritten) is re-read with ordinary loads.
-// Thread (e = lane, g = warp of 16) handles slots k = g, g+16, g+32, g+48; everything else is crypto3's phase 2.
-constexpr int C4_T = 512, C4_G = C4_T / C3_SUB, C4_PER = (HIST + C4_G - 1) / C4_G, C4_STAGES = 3;
-constexpr int C4_STAGE_O = HIST * C3_SUB * 16, C4_STAGE_C = HIST * C3_SUB * 8;  // bytes per stage: 25600 + 12800
-constexpr size_t C4_OFF_STAGE_O = 2 * (size_t)C3_TILE_BYTES;
-constexpr size_t C4_OFF_STAGE_C = C4_OFF_STAGE_O + (size_t)C4_STAGES * C4_STAGE_O;
-constexpr size_t C4_OFF_CUR = C4_OFF_STAGE_C + (size_t)C4_STAGES * C4_STAGE_C;    // double [512]
-constexpr size_t C4_OFF_NEWX = C4_OFF_CUR + (size_t)C4_T * 8;                     // float4 [512]
-constexpr size_t C4_OFF_PORT = C4_OFF_NEWX + (size_t)C4_T * 16;                   // float4 [512]
-constexpr size_t C4_OFF_PM = C4_OFF_PORT + (size_t)C4_T * 16;                     // double [16][32]
-constexpr size_t C4_OFF_PG = C4_OFF_PM + (size_t)C4_T * 8;
-constexpr size_t C4_OFF_LAST = C4_OFF_PG + (size_t)C4_T * 8;                      // double [20][32]
-constexpr size_t C4_OFF_MX = C4_OFF_LAST + (size_t)C3_LAST * C3_SUB * 8;          // float [16][32]
-constexpr size_t C4_OFF_MN = C4_OFF_MX + (size_t)C4_T * 4;
-constexpr size_t C4_OFF_MBAR = C4_OFF_MN + (size_t)C4_T * 4;                      // uint64 [3]
-constexpr size_t C4_OFF_URESET = C4_OFF_MBAR + 32;                                // uint32 [16]
-constexpr size_t C4_SMEM_BYTES = C4_OFF_URESET + C4_G * 4;
-static_assert(C4_SMEM_BYTES <= 227 * 1024, "one CTA per SM: everything has to fit in 227 KB");
-static_assert((size_t)C3_RNGW * C4_T * 4 <= 2 * (size_t)C3_TILE_BYTES, "the Philox table aliases the two tile buffers");
-static_assert(C4_OFF_STAGE_O % 128 == 0 && C4_OFF_STAGE_C % 128 == 0 && C4_STAGE_O % 128 == 0 && C4_STAGE_C % 128 == 0,
-              "TMA destinations are 128-byte aligned");
-
+// ---- mbarrier / TMA wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -864,26 +645,195 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "l"((unsigned long long)map), "r"(x), "r"(y), "r"(bar)
         : "memory");
 }
+// Barrier over the 512 observation threads only (id 1; id 0 is __syncthreads over the whole CTA).
+__device__ __forceinline__ void obs_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(OBS_T) : "memory"); }
+
+// ---- the observation stage ---------------------------------------------------------------------------------------
+struct ObsSmem {
+    const float *stage_o;   // [50][32] x float4 : this unit's open/high/low/volume box
+    const double *stage_c;  // [50][32]          : this unit's close box
+    double *pm, *pg;        // [16][32] MACD-line / signal-line partials
+    float *mx, *mn;         // [16][32] max / min of (close - newest close)
+    double *last;           // [20][32] the last 20 closes
+};
+
+// Thread (e, g): slots k = g + 16 i of env `env` -> tile row `dst`, partial sums -> shared memory.
+// `direct`: read the window with ordinary loads (a reset rewrote it in this call, or there is no TMA stage at all).
+__device__ __forceinline__ void compose_unit(const CArgs &a, const ObsSmem &sm, int e, int g, long long env, bool direct,
+                                             const int (&slot_of)[OBS_PER], uint32_t pitch32, double cur, float4 newest,
+                                             float *dst) {
+    // 1 / cur without the division subroutine: float32 reciprocal + one Newton step in float64 (error ~4e-15)
+    double inv_d = (double)__fdividef(1.0f, (float)cur);
+    inv_d = __fma_rn(inv_d, __fma_rn(-cur, inv_d, 1.0), inv_d);
+    const float inv_f = (float)inv_d;
+    const float4 *so = reinterpret_cast<const float4 *>(sm.stage_o);
+    const float4 *go = reinterpret_cast<const float4 *>(a.st.ohlv) + env;
+    const double *gc = a.st.close + env;
+    double pm = 0.0, pg = 0.0;
+    float mx = 0.0f, mn = 0.0f;  // (the newest close itself contributes 0)
+#pragma unroll
+    for (int i = 0; i < OBS_PER; ++i) {
+        const int k = g + OBS_WARPS * i;
+        if (k < HIST) {
+            float4 x;
+            double c;
+            if (direct) {
+                x = ld_win_f32x4(go + (uint32_t)slot_of[i] * pitch32);
+                c = ld_win_f64(gc + (uint32_t)slot_of[i] * pitch32);
+            } else if (k == HIST - 1) {  // this step's candle: the box may have been fetched before it existed
+                x = newest;
+                c = cur;
+            } else {
+                x = so[slot_of[i] * C3_SUB + e];
+                c = sm.stage_c[slot_of[i] * C3_SUB + e];
+            }
+            dst[k * 5 + 0] = x.x * inv_f;  // price_data / current_price, :513-515
+            dst[k * 5 + 1] = x.y * inv_f;
+            dst[k * 5 + 2] = x.z * inv_f;
+            dst[k * 5 + 3] = (float)(c * inv_d);
+            dst[k * 5 + 4] = x.w * inv_f;
+            const double d = c - cur;
+            pm = __fma_rn(c_macd.wm[k], d, pm);
+            pg = __fma_rn(c_macd.wg[k], d, pg);
+            const float df = (float)d;
+            mx = fmaxf(mx, df);
+            mn = fminf(mn, df);
+            if (k >= HIST - C3_LAST) sm.last[(k - (HIST - C3_LAST)) * C3_SUB + e] = c;
+        }
+    }
+    sm.pm[g * C3_SUB + e] = pm;
+    sm.pg[g * C3_SUB + e] = pg;
+    sm.mx[g * C3_SUB + e] = mx;
+    sm.mn[g * C3_SUB + e] = mn;
+}
+
+template <typename F>
+__device__ __forceinline__ double tree_sum16(F v) {  // sum of v(0..15), depth 4
+    const double a0 = v(0) + v(1), a1 = v(2) + v(3), a2 = v(4) + v(5), a3 = v(6) + v(7);
+    const double a4 = v(8) + v(9), a5 = v(10) + v(11), a6 = v(12) + v(13), a7 = v(14) + v(15);
+    return ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// Warps 0..3 (lane e = env): the 11 features behind the window, features 250..260 of row `dst`.
+__device__ __forceinline__ void finish_unit(const ObsSmem &sm, int e, int g, float4 port, float *dst) {
+    if (g == 0) {  // MACD(12, 26, 9) normalised by the close range, :538-547
+        const double pm = tree_sum16([&](int q) { return sm.pm[q * C3_SUB + e]; });
+        const double pg = tree_sum16([&](int q) { return sm.pg[q * C3_SUB + e]; });
+        float mx = 0.0f, mn = 0.0f;
+#pragma unroll
+        for (int q = 0; q < OBS_WARPS; ++q) {
+            mx = fmaxf(mx, sm.mx[q * C3_SUB + e]);
+            mn = fminf(mn, sm.mn[q * C3_SUB + e]);
+        }
+        const float range = mx - mn;
+        float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
+        if (range > 0.0f) {
+            f0 = __fdividef((float)pm, range);
+            f1 = __fdividef((float)pg, range);
+            f2 = __fdividef((float)(pm - pg), range);
+        }
+        dst[254] = f0;
+        dst[255] = f1;
+        dst[256] = f2;
+    } else if (g == 1) {  // RSI(14) over the last 14 deltas, :45-61; rsi/100 = gain / (gain + loss)
+        const double *wl = sm.last + 5 * C3_SUB + e;  // the last 15 closes
+        auto delta = [&](int i) { return wl[(i + 1) * C3_SUB] - wl[i * C3_SUB]; };
+        const double sg = np_sum<14>([&](int i) { const double d = delta(i); return d > 0 ? d : 0.0; });
+        const double sl = np_sum<14>([&](int i) { const double d = delta(i); return d < 0 ? -d : 0.0; });
+        dst[253] = (sl != 0) ? __fdividef((float)sg, (float)(sg + sl)) : 1.0f;
+    } else if (g == 2) {  // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
+        // Mean and variance of the DIFFERENCES to the newest close (exact subtractions): a window of identical closes
+        // -- a price pinned at the clip bound -- gives sma == close and sd == 0 exactly, like the reference, and the sums
+        // are 4-deep trees instead of NumPy's 8-deep pairwise chains.
+        const double *wl = sm.last + e;
+        const double cur = wl[(C3_LAST - 1) * C3_SUB];
+        auto dv = [&](int i) { return wl[i * C3_SUB] - cur; };
+        const double s = tree_sum16(dv) + ((dv(16) + dv(17)) + (dv(18) + dv(19)));
+        const double mean_d = div20(s);
+        auto sq = [&](int i) { const double t = dv(i) - mean_d; return t * t; };
+        const double var = div20(tree_sum16(sq) + ((sq(16) + sq(17)) + (sq(18) + sq(19))));
+        const float var_f = (float)var;
+        const double sd = (double)(var_f > 0.0f ? var_f * rsqrtf(var_f) : 0.0f);  // float32 accuracy: it only scales features
+        const double sma = cur + mean_d;
+        const double upper = sma + (2 * sd), lower = sma - (2 * sd);
+        const float width = (float)(upper - lower), mid = (float)sma;
+        dst[257] = (upper > lower) ? __fdividef((float)(cur - lower), width) : 0.5f;
+        dst[258] = (sma > 0) ? __fdividef(width, mid) : 0.0f;
+        dst[259] = (sma > 0) ? __fdividef((float)-mean_d, mid) : 0.0f;  // (cur - sma) / sma
+    } else if (g == 3) {  // portfolio features :519-527, psychology :559
+        dst[250] = port.x;
+        dst[251] = port.y;
+        dst[252] = port.z;
+        dst[260] = port.w;
+    }
+}
+
+// One thread: hand the finished tile to the copy engine.
+__device__ __forceinline__ void store_tile(const CArgs &a, const float *tile, long long sub_first) {
+    const long long n_here = min((long long)C3_SUB, a.n - sub_first);
+    const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
+    const uint32_t bulk = bytes & ~15u;
+    if (bulk) bulk_store_s2g(a.io.obs + sub_first * OBS, tile, bulk);
+    bulk_commit();
+    for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[sub_first * OBS + i] = tile[i];  // ragged tail
+}
+
+// ---- shared-memory layouts -----------------------------------------------------------------------------------------
+// common prefix: two tiles, three TMA stages, the observation stage's scratch
+constexpr size_t OFF_STAGE_O = 2 * (size_t)C3_TILE_BYTES;
+constexpr size_t OFF_STAGE_C = OFF_STAGE_O + (size_t)TMA_STAGES * STAGE_O;
+constexpr size_t OFF_PM = OFF_STAGE_C + (size_t)TMA_STAGES * STAGE_C;  // double [16][32]
+constexpr size_t OFF_PG = OFF_PM + (size_t)OBS_T * 8;
+constexpr size_t OFF_LAST = OFF_PG + (size_t)OBS_T * 8;                // double [20][32]
+constexpr size_t OFF_MX = OFF_LAST + (size_t)C3_LAST * C3_SUB * 8;     // float [16][32]
+constexpr size_t OFF_MN = OFF_MX + (size_t)OBS_T * 4;
+constexpr size_t OFF_MBAR = OFF_MN + (size_t)OBS_T * 4;                // uint64 [3 full + 8 ready + 8 freed]
+constexpr size_t OFF_COMMON_END = OFF_MBAR + 8 * 24;
+static_assert(OFF_STAGE_O % 128 == 0 && OFF_STAGE_C % 128 == 0 && STAGE_O % 128 == 0 && STAGE_C % 128 == 0,
+              "TMA destinations are 128-byte aligned");
+
+__device__ __forceinline__ ObsSmem obs_smem(uint8_t *smem_raw, int stage) {
+    ObsSmem sm;
+    sm.stage_o = reinterpret_cast<const float *>(smem_raw + OFF_STAGE_O + (size_t)stage * STAGE_O);
+    sm.stage_c = reinterpret_cast<const double *>(smem_raw + OFF_STAGE_C + (size_t)stage * STAGE_C);
+    sm.pm = reinterpret_cast<double *>(smem_raw + OFF_PM);
+    sm.pg = reinterpret_cast<double *>(smem_raw + OFF_PG);
+    sm.last = reinterpret_cast<double *>(smem_raw + OFF_LAST);
+    sm.mx = reinterpret_cast<float *>(smem_raw + OFF_MX);
+    sm.mn = reinterpret_cast<float *>(smem_raw + OFF_MN);
+    return sm;
+}
+
+// One thread: both boxes of the unit starting at env `env0` into stage `stage`.
+__device__ __forceinline__ void issue_window_loads(uint8_t *smem_raw, int stage, int env0, const CUtensorMap *tm_close,
+                                                   const CUtensorMap *tm_ohlv) {
+    const uint32_t bar = smem_u32(smem_raw + OFF_MBAR) + 8u * stage;
+    mbar_expect_tx(bar, STAGE_O + STAGE_C);
+    tma_load_2d(smem_u32(smem_raw + OFF_STAGE_O + (size_t)stage * STAGE_O), tm_ohlv, env0 * 4, 0, bar);
+    tma_load_2d(smem_u32(smem_raw + OFF_STAGE_C + (size_t)stage * STAGE_C), tm_close, env0, 0, bar);
+}
+
+// ---- crypto4: bulk-synchronous -------------------------------------------------------------------------------------
+constexpr size_t C4_OFF_CUR = OFF_COMMON_END;                        // double [512]
+constexpr size_t C4_OFF_NEWX = C4_OFF_CUR + (size_t)OBS_T * 8;       // float4 [512]
+constexpr size_t C4_OFF_PORT = C4_OFF_NEWX + (size_t)OBS_T * 16;     // float4 [512]
+constexpr size_t C4_OFF_URESET = C4_OFF_PORT + (size_t)OBS_T * 16;   // uint32 [16]
+constexpr size_t C4_SMEM_BYTES = C4_OFF_URESET + OBS_WARPS * 4;
+static_assert(C4_SMEM_BYTES <= 227 * 1024, "one CTA per SM: everything has to fit in 227 KB");
+static_assert((size_t)C3_RNGW * OBS_T * 4 <= 2 * (size_t)C3_TILE_BYTES, "the Philox table aliases the two tile buffers");
 
 template <bool IS_RESET>
-__global__ void __launch_bounds__(C4_T, 1) crypto4_kernel(const CArgs a, const __grid_constant__ CUtensorMap tm_close,
-                                                          const __grid_constant__ CUtensorMap tm_ohlv) {
+__global__ void __launch_bounds__(OBS_T, 1) crypto4_kernel(const CArgs a, const __grid_constant__ CUtensorMap tm_close,
+                                                           const __grid_constant__ CUtensorMap tm_ohlv) {
     constexpr bool USE_TMA = !IS_RESET;  // reset(): every window is rewritten in this launch, nothing to prefetch
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    float *tiles = reinterpret_cast<float *>(smem_raw);                               // [2][32][261]
-    uint32_t *s_rng = reinterpret_cast<uint32_t *>(smem_raw);                         // [20][512], phase 1 only
-    const float *st_o = reinterpret_cast<const float *>(smem_raw + C4_OFF_STAGE_O);   // [3][50][32] x float4
-    const double *st_c = reinterpret_cast<const double *>(smem_raw + C4_OFF_STAGE_C); // [3][50][32]
+    float *tiles = reinterpret_cast<float *>(smem_raw);                        // [2][32][261]
+    uint32_t *s_rng = reinterpret_cast<uint32_t *>(smem_raw);                  // [20][512], dynamics phase only
     double *s_cur = reinterpret_cast<double *>(smem_raw + C4_OFF_CUR);
     float4 *s_newx = reinterpret_cast<float4 *>(smem_raw + C4_OFF_NEWX);
     float4 *s_port = reinterpret_cast<float4 *>(smem_raw + C4_OFF_PORT);
-    double *s_pm = reinterpret_cast<double *>(smem_raw + C4_OFF_PM);
-    double *s_pg = reinterpret_cast<double *>(smem_raw + C4_OFF_PG);
-    double *s_last = reinterpret_cast<double *>(smem_raw + C4_OFF_LAST);
-    float *s_mx = reinterpret_cast<float *>(smem_raw + C4_OFF_MX);
-    float *s_mn = reinterpret_cast<float *>(smem_raw + C4_OFF_MN);
     uint32_t *s_ureset = reinterpret_cast<uint32_t *>(smem_raw + C4_OFF_URESET);
-    const uint32_t mbar0 = smem_u32(smem_raw + C4_OFF_MBAR);
+    const uint32_t mbar0 = smem_u32(smem_raw + OFF_MBAR);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long n = a.n;
@@ -891,31 +841,21 @@ __global__ void __launch_bounds__(C4_T, 1) crypto4_kernel(const CArgs a, const _
     const uint32_t pitch32 = (uint32_t)a.pitch;
     const int head = IS_RESET ? a.p.window_head : (a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1);
     const int oldest = head + 1 == HIST ? 0 : head + 1;
-    const double inv_ib = 1.0 / a.p.initial_balance;
+    const double inv_ib = 1.0 / a.p.initial_balance;  // (features divide by it; the product differs by <= 1 ulp of float64)
     // units of this CTA: u(q) = blockIdx.x + gridDim.x * q, q = 0 .. total-1
     const long long total = n_units > blockIdx.x ? (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto unit_of = [&](long long q) { return (long long)blockIdx.x + (long long)gridDim.x * q; };
 
-    int slot_of[C4_PER];  // ring slot of this thread's i-th candle (k = wid + 16 i, oldest first)
+    int slot_of[OBS_PER];  // ring slot of this thread's i-th candle (k = wid + 16 i, oldest first)
 #pragma unroll
-    for (int i = 0; i < C4_PER; ++i) {
-        int slot = oldest + wid + C4_G * i;
+    for (int i = 0; i < OBS_PER; ++i) {
+        const int slot = oldest + wid + OBS_WARPS * i;
         slot_of[i] = slot >= HIST ? slot - HIST : slot;
     }
-
-    auto issue_loads = [&](long long q) {  // one thread: both boxes of unit u(q) into stage q % 3
-        const int stage = (int)(q % C4_STAGES);
-        const uint32_t bar = mbar0 + 8u * stage;
-        const int env0 = (int)(unit_of(q) * C3_SUB);
-        mbar_expect_tx(bar, C4_STAGE_O + C4_STAGE_C);
-        tma_load_2d(smem_u32(smem_raw + C4_OFF_STAGE_O + (size_t)stage * C4_STAGE_O), &tm_ohlv, env0 * 4, 0, bar);
-        tma_load_2d(smem_u32(smem_raw + C4_OFF_STAGE_C + (size_t)stage * C4_STAGE_C), &tm_close, env0, 0, bar);
-    };
-
     if constexpr (USE_TMA) {
         if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < C4_STAGES; ++s) mbar_init(mbar0 + 8u * s, 1);
+            for (int s = 0; s < TMA_STAGES; ++s) mbar_init(mbar0 + 8u * s, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             fence_proxy_async_smem();
         }
@@ -925,21 +865,20 @@ __global__ void __launch_bounds__(C4_T, 1) crypto4_kernel(const CArgs a, const _
     __syncthreads();
     if constexpr (USE_TMA) {
         if (tid == 0) {
-            for (long long q = 0; q < C4_STAGES && q < total; ++q) issue_loads(q);
+            for (long long q = 0; q < TMA_STAGES && q < total; ++q)
+                issue_window_loads(smem_raw, (int)q, (int)(unit_of(q) * C3_SUB), &tm_close, &tm_ohlv);
         }
     }
 
 #pragma unroll 1
-    for (long long q0 = 0; q0 < total; q0 += C4_G) {
+    for (long long q0 = 0; q0 < total; q0 += OBS_WARPS) {
         // The Philox table of the dynamics phase lives in the tile buffers: the copy engine must have read them.
         if (tid == 0) bulk_wait_read<0>();
         __syncthreads();
-
-        // --------------------------------------------------------------------------------------- phase 1
         {
             const long long qw = q0 + wid;
-            const unsigned resets = dynamics_phase<IS_RESET, C4_T>(
-                a, unit_of(qw), qw < total, head, s_rng,
+            const unsigned resets = dynamics_phase<IS_RESET, OBS_T>(
+                a, unit_of(qw), qw < total, head, s_rng + tid, reinterpret_cast<double *>(s_rng + wid * C3_SUB), OBS_T / 2,
                 [&](double cur, double cash, double holdings, double psych, float4 newest) {
                     const double hv = holdings * cur;  // portfolio features :519-527, psychology :559
                     s_cur[tid] = cur;
@@ -951,132 +890,142 @@ __global__ void __launch_bounds__(C4_T, 1) crypto4_kernel(const CArgs a, const _
         }
         __syncthreads();  // orders this CTA's window writes (the new candle, a reset's whole window) before its reads below
 
-        // --------------------------------------------------------------------------------------- phase 2
-        const int e = lane, g = wid;
 #pragma unroll 1
-        for (int sub = 0; sub < C4_G; ++sub) {
+        for (int sub = 0; sub < OBS_WARPS; ++sub) {
             const long long q = q0 + sub;
             if (q >= total) break;  // CTA-uniform
             const long long sub_first = unit_of(q) * C3_SUB;
-            const long long env = sub_first + e;
-            const int le = sub * C3_SUB + e;  // where phase 1 left this env's values
-            const int stage = (int)(q % C4_STAGES);
+            const long long env = sub_first + lane;
+            const int le = sub * C3_SUB + lane;  // where the dynamics left this env's values
+            const int stage = (int)(q % TMA_STAGES);
             float *tile = tiles + (q & 1) * (C3_SUB * OBS);
-            float *dst = tile + e * OBS;
-            const bool direct = IS_RESET || s_ureset[sub] != 0;  // CTA-uniform: re-read this unit with ordinary loads
-            if constexpr (USE_TMA) mbar_wait(mbar0 + 8u * stage, (uint32_t)((q / C4_STAGES) & 1));  // (keeps the phases in step)
-
-            if (env < n) {
-                const double cur = s_cur[le];
-                // 1 / cur without the division subroutine: float32 reciprocal + one Newton step in float64 (error ~4e-15)
-                double inv_d = (double)__fdividef(1.0f, (float)cur);
-                inv_d = __fma_rn(inv_d, __fma_rn(-cur, inv_d, 1.0), inv_d);
-                const float inv_f = (float)inv_d;
-                const float4 *so = reinterpret_cast<const float4 *>(st_o + (size_t)stage * (C4_STAGE_O / 4));
-                const double *sc = st_c + (size_t)stage * (C4_STAGE_C / 8);
-                const float4 *go = reinterpret_cast<const float4 *>(a.st.ohlv) + env;
-                const double *gc = a.st.close + env;
-                double pm = 0.0, pg = 0.0;
-                float mx = 0.0f, mn = 0.0f;  // (the newest close itself contributes 0)
-#pragma unroll
-                for (int i = 0; i < C4_PER; ++i) {
-                    const int k = g + C4_G * i;
-                    if (k < HIST) {
-                        float4 x;
-                        double c;
-                        if (direct) {
-                            x = ld_win_f32x4(go + (uint32_t)slot_of[i] * pitch32);
-                            c = ld_win_f64(gc + (uint32_t)slot_of[i] * pitch32);
-                        } else if (k == HIST - 1) {  // this step's candle: the box may have been fetched before it existed
-                            x = s_newx[le];
-                            c = cur;
-                        } else {
-                            x = so[slot_of[i] * C3_SUB + e];
-                            c = sc[slot_of[i] * C3_SUB + e];
-                        }
-                        dst[k * 5 + 0] = x.x * inv_f;  // price_data / current_price, :513-515
-                        dst[k * 5 + 1] = x.y * inv_f;
-                        dst[k * 5 + 2] = x.z * inv_f;
-                        dst[k * 5 + 3] = (float)(c * inv_d);
-                        dst[k * 5 + 4] = x.w * inv_f;
-                        const double d = c - cur;
-                        pm = __fma_rn(c_macd.wm[k], d, pm);
-                        pg = __fma_rn(c_macd.wg[k], d, pg);
-                        const float df = (float)d;
-                        mx = fmaxf(mx, df);
-                        mn = fminf(mn, df);
-                        if (k >= HIST - C3_LAST) s_last[(k - (HIST - C3_LAST)) * C3_SUB + e] = c;
-                    }
-                }
-                s_pm[g * C3_SUB + e] = pm;
-                s_pg[g * C3_SUB + e] = pg;
-                s_mx[g * C3_SUB + e] = mx;
-                s_mn[g * C3_SUB + e] = mn;
-            }
+            float *dst = tile + lane * OBS;
+            const ObsSmem sm = obs_smem(smem_raw, stage);
+            const bool direct = IS_RESET || s_ureset[sub] != 0;  // CTA-uniform
+            if constexpr (USE_TMA) mbar_wait(mbar0 + 8u * stage, (uint32_t)((q / TMA_STAGES) & 1));  // (keeps the phases in step)
+            if (env < n) compose_unit(a, sm, lane, wid, env, direct, slot_of, pitch32, s_cur[le], s_newx[le], dst);
             __syncthreads();  // the stage has been consumed; partial sums and the last 20 closes are visible
             if constexpr (USE_TMA) {
-                if (tid == C4_T - 1 && q + C4_STAGES < total) issue_loads(q + C4_STAGES);  // refill the stage just freed
+                if (tid == OBS_T - 1 && q + TMA_STAGES < total)  // refill the stage just freed
+                    issue_window_loads(smem_raw, stage, (int)(unit_of(q + TMA_STAGES) * C3_SUB), &tm_close, &tm_ohlv);
             }
-            if (env < n) {
-                if (g == 0) {  // MACD(12, 26, 9) normalised by the close range, :538-547
-                    double pm = 0.0, pg = 0.0;
-                    float mx = 0.0f, mn = 0.0f;
-#pragma unroll
-                    for (int qq = 0; qq < C4_G; ++qq) {
-                        pm += s_pm[qq * C3_SUB + e];
-                        pg += s_pg[qq * C3_SUB + e];
-                        mx = fmaxf(mx, s_mx[qq * C3_SUB + e]);
-                        mn = fminf(mn, s_mn[qq * C3_SUB + e]);
-                    }
-                    const float range = mx - mn;
-                    float f0 = 0.0f, f1 = 0.0f, f2 = 0.0f;
-                    if (range > 0.0f) {
-                        f0 = __fdividef((float)pm, range);
-                        f1 = __fdividef((float)pg, range);
-                        f2 = __fdividef((float)(pm - pg), range);
-                    }
-                    dst[254] = f0;
-                    dst[255] = f1;
-                    dst[256] = f2;
-                } else if (g == 1) {  // RSI(14) over the last 14 deltas, :45-61; rsi/100 = gain / (gain + loss)
-                    const double *wl = s_last + 5 * C3_SUB + e;  // the last 15 closes
-                    auto delta = [&](int i) { return wl[(i + 1) * C3_SUB] - wl[i * C3_SUB]; };
-                    const double sg = np_sum<14>([&](int i) { const double d = delta(i); return d > 0 ? d : 0.0; });
-                    const double sl = np_sum<14>([&](int i) { const double d = delta(i); return d < 0 ? -d : 0.0; });
-                    dst[253] = (sl != 0) ? __fdividef((float)sg, (float)(sg + sl)) : 1.0f;
-                } else if (g == 2) {  // Bollinger(20, 2 sigma, population std), :64-77 and :550-554
-                    const double *wl = s_last + e;
-                    const double sma = div20(np_sum<C3_LAST>([&](int i) { return wl[i * C3_SUB]; }));  // exact mean
-                    const double var = np_sum<C3_LAST>([&](int i) { const double d = wl[i * C3_SUB] - sma; return d * d; });
-                    const float var_f = (float)div20(var);
-                    const double sd = (double)(var_f > 0.0f ? var_f * rsqrtf(var_f) : 0.0f);
-                    const double upper = sma + (2 * sd), lower = sma - (2 * sd), cur = wl[(C3_LAST - 1) * C3_SUB];
-                    const float width = (float)(upper - lower), mid = (float)sma;
-                    dst[257] = (upper > lower) ? __fdividef((float)(cur - lower), width) : 0.5f;
-                    dst[258] = (sma > 0) ? __fdividef(width, mid) : 0.0f;
-                    dst[259] = (sma > 0) ? __fdividef((float)(cur - sma), mid) : 0.0f;
-                } else if (g == 3) {
-                    const float4 pf = s_port[le];
-                    dst[250] = pf.x;
-                    dst[251] = pf.y;
-                    dst[252] = pf.z;
-                    dst[260] = pf.w;
-                }
-            }
+            if (env < n && wid < 4) finish_unit(sm, lane, wid, s_port[le], dst);
             fence_proxy_async_smem();
             if (tid == 0) bulk_wait_read<0>();  // the copy issued one unit ago has read the other tile buffer
             __syncthreads();
-            if (tid == 0) {
-                const long long n_here = min((long long)C3_SUB, n - sub_first);
-                const uint32_t bytes = (uint32_t)(n_here * OBS * sizeof(float));
-                const uint32_t bulk = bytes & ~15u;
-                if (bulk) bulk_store_s2g(a.io.obs + sub_first * OBS, tile, bulk);
-                bulk_commit();
-                for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[sub_first * OBS + i] = tile[i];  // ragged tail
-            }
+            if (tid == 0) store_tile(a, tile, sub_first);
         }
     }
     if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the copy engine's reads
+}
+
+// ---- crypto5: warp-specialised -------------------------------------------------------------------------------------
+constexpr int DYN_WARPS = 8, C5_T = OBS_T + DYN_WARPS * 32;      // 768 threads = 6 warpgroups (4 observation + 2 dynamics)
+// setmaxnreg moves registers inside the CTA's OWN pool (what it was launched with: 768 threads x 80), it cannot draw on
+// the rest of the register file: 512 * 64 + 256 * 112 = 61440 = 768 * 80.
+constexpr int C5_LAUNCH_REGS = 80, C5_REGS_OBS = 64, C5_REGS_DYN = 112;
+static_assert(OBS_T * C5_REGS_OBS + DYN_WARPS * 32 * C5_REGS_DYN <= C5_T * C5_LAUNCH_REGS, "setmaxnreg budget");
+constexpr size_t C5_OFF_CUR = OFF_COMMON_END;                                   // double [8][32]   ring slot = dynamics warp
+constexpr size_t C5_OFF_NEWX = C5_OFF_CUR + (size_t)DYN_WARPS * C3_SUB * 8;     // float4 [8][32]
+constexpr size_t C5_OFF_PORT = C5_OFF_NEWX + (size_t)DYN_WARPS * C3_SUB * 16;   // float4 [8][32]
+constexpr size_t C5_OFF_URESET = C5_OFF_PORT + (size_t)DYN_WARPS * C3_SUB * 16; // uint32 [8]
+constexpr size_t C5_OFF_RNG = C5_OFF_URESET + 128;                              // uint32 [8][20][32]
+constexpr size_t C5_SMEM_BYTES = C5_OFF_RNG + (size_t)DYN_WARPS * C3_RNGW * C3_SUB * 4;
+static_assert(C5_SMEM_BYTES <= 227 * 1024, "one CTA per SM: everything has to fit in 227 KB");
+
+__global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const __grid_constant__ CUtensorMap tm_close,
+                                                          const __grid_constant__ CUtensorMap tm_ohlv) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float *tiles = reinterpret_cast<float *>(smem_raw);  // [2][32][261]
+    double *s_cur = reinterpret_cast<double *>(smem_raw + C5_OFF_CUR);
+    float4 *s_newx = reinterpret_cast<float4 *>(smem_raw + C5_OFF_NEWX);
+    float4 *s_port = reinterpret_cast<float4 *>(smem_raw + C5_OFF_PORT);
+    uint32_t *s_ureset = reinterpret_cast<uint32_t *>(smem_raw + C5_OFF_URESET);
+    const uint32_t mbar_full = smem_u32(smem_raw + OFF_MBAR);   // [3]  TMA stage filled
+    const uint32_t mbar_ready = mbar_full + 8u * TMA_STAGES;    // [8]  ring slot filled by its dynamics warp
+    const uint32_t mbar_freed = mbar_ready + 8u * DYN_WARPS;    // [8]  ring slot consumed by the observation warps
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long n = a.n;
+    const long long n_units = (n + C3_SUB - 1) / C3_SUB;
+    const int head = a.p.window_head + 1 == HIST ? 0 : a.p.window_head + 1;
+    const long long total = n_units > blockIdx.x ? (n_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto unit_of = [&](long long q) { return (long long)blockIdx.x + (long long)gridDim.x * q; };
+
+    if (tid == 0) {
+        for (int s = 0; s < TMA_STAGES + 2 * DYN_WARPS; ++s) mbar_init(mbar_full + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async_smem();
+    }
+    pdl_launch_dependents();  // the next step's grid may become resident as this one drains ...
+    pdl_wait();               // ... and this one touches nothing before the previous step's grid has flushed
+    __syncthreads();          // (the only CTA-wide barrier: the two roles part ways here)
+
+    if (wid >= OBS_WARPS) {
+        // =================================================================================== dynamics warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C5_REGS_DYN));
+        const int dw = wid - OBS_WARPS;  // this warp's ring slot
+        const double inv_ib = 1.0 / a.p.initial_balance;
+        uint32_t *table = reinterpret_cast<uint32_t *>(smem_raw + C5_OFF_RNG) + dw * (C3_RNGW * C3_SUB);  // [20][32]
+        const int slot = dw * C3_SUB + lane;
+#pragma unroll 1
+        for (long long q = dw; q < total; q += DYN_WARPS) {
+            const long long use = q / DYN_WARPS;  // how often this slot has been filled before
+            if (use > 0) mbar_wait(mbar_freed + 8u * dw, (uint32_t)((use - 1) & 1));
+            const unsigned resets = dynamics_phase<false, C3_SUB>(
+                a, unit_of(q), true, head, table + lane, reinterpret_cast<double *>(table), C3_SUB / 2,
+                [&](double cur, double cash, double holdings, double psych, float4 newest) {
+                    const double hv = holdings * cur;  // portfolio features :519-527, psychology :559
+                    s_cur[slot] = cur;
+                    s_newx[slot] = newest;
+                    s_port[slot] = make_float4((float)(cash * inv_ib), (float)(hv * inv_ib), (float)((cash + hv) * inv_ib),
+                                               (float)psych);
+                });
+            if (lane == 0) s_ureset[dw] = resets;
+            __syncwarp();  // every lane's shared- and global-memory writes are ordered before the release below
+            if (lane == 0) mbar_arrive(mbar_ready + 8u * dw);
+        }
+    } else {
+        // =================================================================================== observation warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C5_REGS_OBS));
+        const uint32_t pitch32 = (uint32_t)a.pitch;
+        const int oldest = head + 1 == HIST ? 0 : head + 1;
+        int slot_of[OBS_PER];  // ring slot of this thread's i-th candle (k = wid + 16 i, oldest first)
+#pragma unroll
+        for (int i = 0; i < OBS_PER; ++i) {
+            const int slot = oldest + wid + OBS_WARPS * i;
+            slot_of[i] = slot >= HIST ? slot - HIST : slot;
+        }
+        if (tid == 0) {
+            for (long long q = 0; q < TMA_STAGES && q < total; ++q)
+                issue_window_loads(smem_raw, (int)q, (int)(unit_of(q) * C3_SUB), &tm_close, &tm_ohlv);
+        }
+#pragma unroll 1
+        for (long long q = 0; q < total; ++q) {
+            const long long sub_first = unit_of(q) * C3_SUB;
+            const long long env = sub_first + lane;
+            const int dw = (int)(q % DYN_WARPS);
+            const int le = dw * C3_SUB + lane;
+            const int stage = (int)(q % TMA_STAGES);
+            float *tile = tiles + (q & 1) * (C3_SUB * OBS);
+            float *dst = tile + lane * OBS;
+            const ObsSmem sm = obs_smem(smem_raw, stage);
+            mbar_wait(mbar_ready + 8u * dw, (uint32_t)((q / DYN_WARPS) & 1));   // the unit's dynamics are done
+            mbar_wait(mbar_full + 8u * stage, (uint32_t)((q / TMA_STAGES) & 1));  // its window box has landed
+            const bool direct = s_ureset[dw] != 0;  // uniform over the 16 warps
+            if (env < n) compose_unit(a, sm, lane, wid, env, direct, slot_of, pitch32, s_cur[le], s_newx[le], dst);
+            obs_bar_sync();  // the stage has been consumed; partial sums and the last 20 closes are visible
+            if (tid == OBS_T - 1 && q + TMA_STAGES < total)  // refill the stage just freed
+                issue_window_loads(smem_raw, stage, (int)(unit_of(q + TMA_STAGES) * C3_SUB), &tm_close, &tm_ohlv);
+            if (env < n && wid < 4) finish_unit(sm, lane, wid, s_port[le], dst);
+            fence_proxy_async_smem();
+            if (tid == 0) bulk_wait_read<0>();  // the copy issued one unit ago has read the other tile buffer
+            obs_bar_sync();
+            if (tid == 0) store_tile(a, tile, sub_first);
+            if (tid == 32) mbar_arrive(mbar_freed + 8u * dw);  // every read of the ring slot is behind the barrier above
+        }
+        if (tid == 0) bulk_wait_read<0>();  // shared memory must outlive the copy engine's reads
+    }
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (libbeng does not link libcuda).
@@ -1109,22 +1058,21 @@ int make_window_map(CUtensorMap *map, void *base, long long pitch, CUtensorMapDa
     return r == CUDA_SUCCESS ? 0 : BENG_ERR_BAD_ARG;
 }
 
-template <bool IS_RESET>
-int launch4(const CArgs &a, cudaStream_t stream) {
+template <typename Kern>
+int launch_tma(Kern kern, int threads, size_t smem, const CArgs &a, cudaStream_t stream) {
     CUtensorMap tm_close, tm_ohlv;
     if (int rc = make_window_map(&tm_close, a.st.close, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, 1)) return rc;
     if (int rc = make_window_map(&tm_ohlv, a.st.ohlv, a.pitch, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 4)) return rc;
-    auto kern = crypto4_kernel<IS_RESET>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C4_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     const long long n_units = (a.n + C3_SUB - 1) / C3_SUB;
-    long long grid = device_sm_count();
+    long long grid = device_sm_count();  // one persistent CTA per SM
     if (grid > n_units) grid = n_units;
     static const bool use_pdl = getenv("BENG_NO_PDL") == nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(C4_T);
-    cfg.dynamicSmemBytes = C4_SMEM_BYTES;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1138,21 +1086,17 @@ int launch4(const CArgs &a, cudaStream_t stream) {
 
 template <bool IS_RESET>
 int launch(const CArgs &a, cudaStream_t stream) {
-    // BENG_CRYPTO_VARIANT (read once): 0 = crypto3 two tile buffers + register prefetch, 2 CTAs/SM (default);
-    // 1 = one buffer, no prefetch, 3 CTAs/SM; 2 = two buffers, no prefetch, 2 CTAs/SM; 3 = one buffer, no prefetch,
-    // 4 CTAs/SM.
-    static int variant = -1;
-    if (variant < 0) {
-        const char *v = getenv("BENG_CRYPTO_VARIANT");
-        variant = v ? atoi(v) : 0;
-    }
-    switch (variant) {
-        case 1: return launch3<IS_RESET, 1, false, 3>(a, stream);
-        case 2: return launch3<IS_RESET, 2, false, 2>(a, stream);
-        case 3: return launch3<IS_RESET, 1, false, 4>(a, stream);
-        case 4: return launch3<IS_RESET, 1, true, 3>(a, stream);
-        case 7: return launch4<IS_RESET>(a, stream);
-        default: return launch3<IS_RESET, 2, true, 2>(a, stream);
+    // reset(): the bulk-synchronous kernel (every window is rewritten, nothing to prefetch or to run ahead of).
+    // step(): the warp-specialised kernel; BENG_CRYPTO_VARIANT=4 (read once) selects the bulk-synchronous one for A/Bs.
+    if constexpr (IS_RESET) {
+        return launch_tma(crypto4_kernel<true>, OBS_T, C4_SMEM_BYTES, a, stream);
+    } else {
+        static const int variant = [] {
+            const char *v = getenv("BENG_CRYPTO_VARIANT");
+            return v ? atoi(v) : 5;
+        }();
+        if (variant == 4) return launch_tma(crypto4_kernel<false>, OBS_T, C4_SMEM_BYTES, a, stream);
+        return launch_tma(crypto5_kernel, C5_T, C5_SMEM_BYTES, a, stream);
     }
 }
 
