@@ -638,6 +638,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// Same wait for a warp that expects to wait LONG (a dynamics warp running ahead of the observation warps): back off
+// between polls so that the spin does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(256);
+    }
+}
 // One [rows][box_w] box of a 2-D tensor (tensor map in kernel-parameter space) -> shared memory, completion on `bar`.
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar) {
     asm volatile(
@@ -658,8 +676,10 @@ struct ObsSmem {
 };
 
 // Thread (e, g): slots k = g + 16 i of env `env` -> tile row `dst`, partial sums -> shared memory.
-// `direct`: read the window with ordinary loads (a reset rewrote it in this call, or there is no TMA stage at all).
-__device__ __forceinline__ void compose_unit(const CArgs &a, const ObsSmem &sm, int e, int g, long long env, bool direct,
+// DIRECT: read the window with ordinary loads (a reset rewrote it in this call, or there is no TMA stage at all); a
+// separate instantiation, so that the common path carries none of its (predicated-off, but still issued) instructions.
+template <bool DIRECT>
+__device__ __forceinline__ void compose_unit(const CArgs &a, const ObsSmem &sm, int e, int g, long long env,
                                              const int (&slot_of)[OBS_PER], uint32_t pitch32, double cur, float4 newest,
                                              float *dst) {
     // 1 / cur without the division subroutine: float32 reciprocal + one Newton step in float64 (error ~4e-15)
@@ -677,7 +697,7 @@ __device__ __forceinline__ void compose_unit(const CArgs &a, const ObsSmem &sm, 
         if (k < HIST) {
             float4 x;
             double c;
-            if (direct) {
+            if constexpr (DIRECT) {
                 x = ld_win_f32x4(go + (uint32_t)slot_of[i] * pitch32);
                 c = ld_win_f64(gc + (uint32_t)slot_of[i] * pitch32);
             } else if (k == HIST - 1) {  // this step's candle: the box may have been fetched before it existed
@@ -903,7 +923,10 @@ __global__ void __launch_bounds__(OBS_T, 1) crypto4_kernel(const CArgs a, const 
             const ObsSmem sm = obs_smem(smem_raw, stage);
             const bool direct = IS_RESET || s_ureset[sub] != 0;  // CTA-uniform
             if constexpr (USE_TMA) mbar_wait(mbar0 + 8u * stage, (uint32_t)((q / TMA_STAGES) & 1));  // (keeps the phases in step)
-            if (env < n) compose_unit(a, sm, lane, wid, env, direct, slot_of, pitch32, s_cur[le], s_newx[le], dst);
+            if (env < n) {
+                if (direct) compose_unit<true>(a, sm, lane, wid, env, slot_of, pitch32, s_cur[le], s_newx[le], dst);
+                else compose_unit<false>(a, sm, lane, wid, env, slot_of, pitch32, s_cur[le], s_newx[le], dst);
+            }
             __syncthreads();  // the stage has been consumed; partial sums and the last 20 closes are visible
             if constexpr (USE_TMA) {
                 if (tid == OBS_T - 1 && q + TMA_STAGES < total)  // refill the stage just freed
@@ -920,10 +943,15 @@ __global__ void __launch_bounds__(OBS_T, 1) crypto4_kernel(const CArgs a, const 
 }
 
 // ---- crypto5: warp-specialised -------------------------------------------------------------------------------------
+#ifndef BENG_C5_OBS_REGS
+#define BENG_C5_OBS_REGS 72
+#define BENG_C5_DYN_REGS 96
+#endif
 constexpr int DYN_WARPS = 8, C5_T = OBS_T + DYN_WARPS * 32;      // 768 threads = 6 warpgroups (4 observation + 2 dynamics)
 // setmaxnreg moves registers inside the CTA's OWN pool (what it was launched with: 768 threads x 80), it cannot draw on
-// the rest of the register file: 512 * 64 + 256 * 112 = 61440 = 768 * 80.
-constexpr int C5_LAUNCH_REGS = 80, C5_REGS_OBS = 64, C5_REGS_DYN = 112;
+// the rest of the register file: 512 * 72 + 256 * 96 = 61440 = 768 * 80 (the dynamics warps have slack, the observation
+// warps are issue-bound and want their index arithmetic in registers).
+constexpr int C5_LAUNCH_REGS = 80, C5_REGS_OBS = BENG_C5_OBS_REGS, C5_REGS_DYN = BENG_C5_DYN_REGS;
 static_assert(OBS_T * C5_REGS_OBS + DYN_WARPS * 32 * C5_REGS_DYN <= C5_T * C5_LAUNCH_REGS, "setmaxnreg budget");
 constexpr size_t C5_OFF_CUR = OFF_COMMON_END;                                   // double [8][32]   ring slot = dynamics warp
 constexpr size_t C5_OFF_NEWX = C5_OFF_CUR + (size_t)DYN_WARPS * C3_SUB * 8;     // float4 [8][32]
@@ -971,7 +999,7 @@ __global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const _
 #pragma unroll 1
         for (long long q = dw; q < total; q += DYN_WARPS) {
             const long long use = q / DYN_WARPS;  // how often this slot has been filled before
-            if (use > 0) mbar_wait(mbar_freed + 8u * dw, (uint32_t)((use - 1) & 1));
+            if (use > 0) mbar_wait_backoff(mbar_freed + 8u * dw, (uint32_t)((use - 1) & 1));
             const unsigned resets = dynamics_phase<false, C3_SUB>(
                 a, unit_of(q), true, head, table + lane, reinterpret_cast<double *>(table), C3_SUB / 2,
                 [&](double cur, double cash, double holdings, double psych, float4 newest) {
@@ -1013,7 +1041,10 @@ __global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const _
             mbar_wait(mbar_ready + 8u * dw, (uint32_t)((q / DYN_WARPS) & 1));   // the unit's dynamics are done
             mbar_wait(mbar_full + 8u * stage, (uint32_t)((q / TMA_STAGES) & 1));  // its window box has landed
             const bool direct = s_ureset[dw] != 0;  // uniform over the 16 warps
-            if (env < n) compose_unit(a, sm, lane, wid, env, direct, slot_of, pitch32, s_cur[le], s_newx[le], dst);
+            if (env < n) {
+                if (direct) compose_unit<true>(a, sm, lane, wid, env, slot_of, pitch32, s_cur[le], s_newx[le], dst);
+                else compose_unit<false>(a, sm, lane, wid, env, slot_of, pitch32, s_cur[le], s_newx[le], dst);
+            }
             obs_bar_sync();  // the stage has been consumed; partial sums and the last 20 closes are visible
             if (tid == OBS_T - 1 && q + TMA_STAGES < total)  // refill the stage just freed
                 issue_window_loads(smem_raw, stage, (int)(unit_of(q + TMA_STAGES) * C3_SUB), &tm_close, &tm_ohlv);
