@@ -394,8 +394,9 @@ def kernel_description(lib, env_name, n):
         return (f"beng::snake_kernel<T={t_.value},STAGES={s_.value},IS_RESET=false,OWNROW=true>, "
                 f"{c_.value} persistent CTAs/SM")
     if env_name == "crypto":
-        return ("beng::crypto3_kernel<IS_RESET=false>: persistent 256-thread CTAs over 32-env units; per-env float64 "
-                "dynamics, then the window is streamed once (indicators accumulated on the way) into the 261-feature tile")
+        return ("beng::crypto5_kernel: warp-specialised, 768 threads, 1 persistent CTA/SM: 8 dynamics warps (float64 "
+                "state chain, 112 regs) run up to 16 units ahead of 16 observation warps (64 regs) that compose the 261-float "
+                "rows from a 2-stage TMA tensor-load ring and drain 32-env tiles with bulk stores")
     if env_name == "climate":
         return "beng::climate_kernel<T=128,IS_RESET=false>: one thread per env, 128-env tile per CTA, 8 CTAs per SM"
     if env_name == "builder":

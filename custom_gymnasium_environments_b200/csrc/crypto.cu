@@ -332,16 +332,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 // price walk, psychology, reward).  What does not: the 11 indicator features, float32 outputs checked at rtol 1e-5 /
 // atol 1e-6 (tests/test_crypto_gpu.py); their error against the oracle is ~1e-7.
 //
-// The window comes in through the TMA: a ring of three 38.4 KB shared-memory stages filled by cp.async.bulk.tensor (one
+// The window comes in through the TMA: a ring of two 38.4 KB shared-memory stages filled by cp.async.bulk.tensor (one
 // [50 slots][32 envs] box of the close tensor and one of the open/high/low/volume tensor per unit, completion on an
-// mbarrier), so 115 KB per SM are in flight whatever the threads are doing.  What a box fetched early cannot contain is
+// mbarrier), so the next unit's window is in flight whatever the threads are doing.  What a box fetched early cannot contain is
 // handled explicitly: the newest candle (written by the dynamics after the box may have been read) comes from shared
 // memory, and a unit in which some env reset in this call (its whole window was rewritten) is re-read with ordinary loads.
 //
 // Two kernels share these stages:
 //   crypto5_kernel (the step)  warp-specialised, 768 threads, one CTA per SM: 16 OBSERVATION warps (64 registers after
-//       setmaxnreg.dec) and 8 DYNAMICS warps (112 registers after setmaxnreg.inc) that run up to 8 units ahead; a
-//       dynamics warp hands its unit over through its slot of an 8-deep shared-memory ring (mbarriers ready[]/freed[]).
+//       setmaxnreg.dec) and 8 DYNAMICS warps (112 registers after setmaxnreg.inc) that run up to 16 units ahead; a
+//       dynamics warp hands its unit over through a slot of a 16-deep shared-memory ring (mbarriers ready[]/freed[]).
 //       The ~13,000-cycle dependency chain of a unit's dynamics therefore never sits on the observation path
 //       (in the bulk-synchronous kernel it was 29 % of the step, profiles/crypto_step_r2_ncu_summary.txt).
 //   crypto4_kernel (reset(), and BENG_CRYPTO_VARIANT=4 for A/B)  bulk-synchronous, 512 threads: rounds of 16 units,
@@ -352,7 +352,13 @@ constexpr int C3_LAST = 20;     // closes kept for Bollinger / RSI
 constexpr int C3_COOP_MAX = 8;  // resets per warp up to which each one is rebuilt by the whole warp
 constexpr int C3_TILE_BYTES = C3_SUB * OBS * (int)sizeof(float);
 static_assert(C3_TILE_BYTES % 128 == 0, "tile buffers stay 128-byte aligned");
-constexpr int OBS_WARPS = 16, OBS_T = OBS_WARPS * 32, OBS_PER = (HIST + OBS_WARPS - 1) / OBS_WARPS, TMA_STAGES = 3;
+#ifndef BENG_TMA_STAGES
+#define BENG_TMA_STAGES 2  /* measured: 2 stages = 3 stages (133 vs 136 us); the third one buys nothing */
+#endif
+#ifndef BENG_C5_RING
+#define BENG_C5_RING 16  /* measured: 8 slots 133-144 us, 16 slots 126-133 us (the dynamics warps run further ahead) */
+#endif
+constexpr int OBS_WARPS = 16, OBS_T = OBS_WARPS * 32, OBS_PER = (HIST + OBS_WARPS - 1) / OBS_WARPS, TMA_STAGES = BENG_TMA_STAGES;
 constexpr int STAGE_O = HIST * C3_SUB * 16, STAGE_C = HIST * C3_SUB * 8;  // bytes per stage: 25600 + 12800
 
 struct MacdWeights {
@@ -808,7 +814,7 @@ constexpr size_t OFF_LAST = OFF_PG + (size_t)OBS_T * 8;                // double
 constexpr size_t OFF_MX = OFF_LAST + (size_t)C3_LAST * C3_SUB * 8;     // float [16][32]
 constexpr size_t OFF_MN = OFF_MX + (size_t)OBS_T * 4;
 constexpr size_t OFF_MBAR = OFF_MN + (size_t)OBS_T * 4;                // uint64 [3 full + 8 ready + 8 freed]
-constexpr size_t OFF_COMMON_END = OFF_MBAR + 8 * 24;
+constexpr size_t OFF_COMMON_END = OFF_MBAR + 8 * 40;
 static_assert(OFF_STAGE_O % 128 == 0 && OFF_STAGE_C % 128 == 0 && STAGE_O % 128 == 0 && STAGE_C % 128 == 0,
               "TMA destinations are 128-byte aligned");
 
@@ -944,19 +950,20 @@ __global__ void __launch_bounds__(OBS_T, 1) crypto4_kernel(const CArgs a, const 
 
 // ---- crypto5: warp-specialised -------------------------------------------------------------------------------------
 #ifndef BENG_C5_OBS_REGS
-#define BENG_C5_OBS_REGS 72
-#define BENG_C5_DYN_REGS 96
+#define BENG_C5_OBS_REGS 64  /* measured: 64 / 112 is 3 us faster than 72 / 96 */
+#define BENG_C5_DYN_REGS 112
 #endif
 constexpr int DYN_WARPS = 8, C5_T = OBS_T + DYN_WARPS * 32;      // 768 threads = 6 warpgroups (4 observation + 2 dynamics)
 // setmaxnreg moves registers inside the CTA's OWN pool (what it was launched with: 768 threads x 80), it cannot draw on
-// the rest of the register file: 512 * 72 + 256 * 96 = 61440 = 768 * 80 (the dynamics warps have slack, the observation
-// warps are issue-bound and want their index arithmetic in registers).
+// the rest of the register file: 512 * 64 + 256 * 112 = 61440 = 768 * 80.
 constexpr int C5_LAUNCH_REGS = 80, C5_REGS_OBS = BENG_C5_OBS_REGS, C5_REGS_DYN = BENG_C5_DYN_REGS;
 static_assert(OBS_T * C5_REGS_OBS + DYN_WARPS * 32 * C5_REGS_DYN <= C5_T * C5_LAUNCH_REGS, "setmaxnreg budget");
-constexpr size_t C5_OFF_CUR = OFF_COMMON_END;                                   // double [8][32]   ring slot = dynamics warp
-constexpr size_t C5_OFF_NEWX = C5_OFF_CUR + (size_t)DYN_WARPS * C3_SUB * 8;     // float4 [8][32]
-constexpr size_t C5_OFF_PORT = C5_OFF_NEWX + (size_t)DYN_WARPS * C3_SUB * 16;   // float4 [8][32]
-constexpr size_t C5_OFF_URESET = C5_OFF_PORT + (size_t)DYN_WARPS * C3_SUB * 16; // uint32 [8]
+constexpr int C5_RING = BENG_C5_RING;  // hand-over slots: unit q uses slot q % C5_RING (a multiple of DYN_WARPS)
+static_assert(C5_RING % DYN_WARPS == 0 && C5_RING <= 16, "each dynamics warp owns C5_RING / DYN_WARPS slots");
+constexpr size_t C5_OFF_CUR = OFF_COMMON_END;                                 // double [ring][32]
+constexpr size_t C5_OFF_NEWX = C5_OFF_CUR + (size_t)C5_RING * C3_SUB * 8;     // float4 [ring][32]
+constexpr size_t C5_OFF_PORT = C5_OFF_NEWX + (size_t)C5_RING * C3_SUB * 16;   // float4 [ring][32]
+constexpr size_t C5_OFF_URESET = C5_OFF_PORT + (size_t)C5_RING * C3_SUB * 16; // uint32 [ring]
 constexpr size_t C5_OFF_RNG = C5_OFF_URESET + 128;                              // uint32 [8][20][32]
 constexpr size_t C5_SMEM_BYTES = C5_OFF_RNG + (size_t)DYN_WARPS * C3_RNGW * C3_SUB * 4;
 static_assert(C5_SMEM_BYTES <= 227 * 1024, "one CTA per SM: everything has to fit in 227 KB");
@@ -970,8 +977,8 @@ __global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const _
     float4 *s_port = reinterpret_cast<float4 *>(smem_raw + C5_OFF_PORT);
     uint32_t *s_ureset = reinterpret_cast<uint32_t *>(smem_raw + C5_OFF_URESET);
     const uint32_t mbar_full = smem_u32(smem_raw + OFF_MBAR);   // [3]  TMA stage filled
-    const uint32_t mbar_ready = mbar_full + 8u * TMA_STAGES;    // [8]  ring slot filled by its dynamics warp
-    const uint32_t mbar_freed = mbar_ready + 8u * DYN_WARPS;    // [8]  ring slot consumed by the observation warps
+    const uint32_t mbar_ready = mbar_full + 8u * TMA_STAGES;    // [ring] slot filled by its dynamics warp
+    const uint32_t mbar_freed = mbar_ready + 8u * C5_RING;      // [ring] slot consumed by the observation warps
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long n = a.n;
@@ -981,7 +988,7 @@ __global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const _
     auto unit_of = [&](long long q) { return (long long)blockIdx.x + (long long)gridDim.x * q; };
 
     if (tid == 0) {
-        for (int s = 0; s < TMA_STAGES + 2 * DYN_WARPS; ++s) mbar_init(mbar_full + 8u * s, 1);
+        for (int s = 0; s < TMA_STAGES + 2 * C5_RING; ++s) mbar_init(mbar_full + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async_smem();
     }
@@ -995,11 +1002,12 @@ __global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const _
         const int dw = wid - OBS_WARPS;  // this warp's ring slot
         const double inv_ib = 1.0 / a.p.initial_balance;
         uint32_t *table = reinterpret_cast<uint32_t *>(smem_raw + C5_OFF_RNG) + dw * (C3_RNGW * C3_SUB);  // [20][32]
-        const int slot = dw * C3_SUB + lane;
 #pragma unroll 1
         for (long long q = dw; q < total; q += DYN_WARPS) {
-            const long long use = q / DYN_WARPS;  // how often this slot has been filled before
-            if (use > 0) mbar_wait_backoff(mbar_freed + 8u * dw, (uint32_t)((use - 1) & 1));
+            const int rs = (int)(q % C5_RING);    // ring slot of this unit
+            const int slot = rs * C3_SUB + lane;
+            const long long use = q / C5_RING;    // how often this slot has been filled before
+            if (use > 0) mbar_wait_backoff(mbar_freed + 8u * rs, (uint32_t)((use - 1) & 1));
             const unsigned resets = dynamics_phase<false, C3_SUB>(
                 a, unit_of(q), true, head, table + lane, reinterpret_cast<double *>(table), C3_SUB / 2,
                 [&](double cur, double cash, double holdings, double psych, float4 newest) {
@@ -1009,9 +1017,9 @@ __global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const _
                     s_port[slot] = make_float4((float)(cash * inv_ib), (float)(hv * inv_ib), (float)((cash + hv) * inv_ib),
                                                (float)psych);
                 });
-            if (lane == 0) s_ureset[dw] = resets;
+            if (lane == 0) s_ureset[rs] = resets;
             __syncwarp();  // every lane's shared- and global-memory writes are ordered before the release below
-            if (lane == 0) mbar_arrive(mbar_ready + 8u * dw);
+            if (lane == 0) mbar_arrive(mbar_ready + 8u * rs);
         }
     } else {
         // =================================================================================== observation warps
@@ -1032,13 +1040,13 @@ __global__ void __launch_bounds__(C5_T, 1) crypto5_kernel(const CArgs a, const _
         for (long long q = 0; q < total; ++q) {
             const long long sub_first = unit_of(q) * C3_SUB;
             const long long env = sub_first + lane;
-            const int dw = (int)(q % DYN_WARPS);
+            const int dw = (int)(q % C5_RING);  // ring slot of this unit
             const int le = dw * C3_SUB + lane;
             const int stage = (int)(q % TMA_STAGES);
             float *tile = tiles + (q & 1) * (C3_SUB * OBS);
             float *dst = tile + lane * OBS;
             const ObsSmem sm = obs_smem(smem_raw, stage);
-            mbar_wait(mbar_ready + 8u * dw, (uint32_t)((q / DYN_WARPS) & 1));   // the unit's dynamics are done
+            mbar_wait(mbar_ready + 8u * dw, (uint32_t)((q / C5_RING) & 1));     // the unit's dynamics are done
             mbar_wait(mbar_full + 8u * stage, (uint32_t)((q / TMA_STAGES) & 1));  // its window box has landed
             const bool direct = s_ureset[dw] != 0;  // uniform over the 16 warps
             if (env < n) {
