@@ -6,6 +6,7 @@ snapshot; it is git-ignored (*.so).  nvcc cross-compiles for sm_100a without a G
 from __future__ import annotations
 
 import glob
+import hashlib
 import os
 import shutil
 import subprocess
@@ -28,11 +29,26 @@ def _deps():
     return sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(PKG_DIR, "..", "include", "*.h"))
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash() -> str:
+    """sha256 over the compile flags and every source the library is built from (content, not mtimes: the snapshot that
+    carries the library to the GPU box does not preserve them)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(_deps()):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """True when libbeng.so is missing or was built from different sources / flags than the ones in the tree."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(f) > t for f in _deps())
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -48,6 +64,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash() + "\n")
     if verbose:
         print(res.stderr)
     return LIB_PATH

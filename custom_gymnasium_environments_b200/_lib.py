@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._build import LIB_PATH
+from ._build import LIB_PATH, is_stale
 
 _lib = None
 
@@ -151,6 +151,11 @@ def load():
                 f"{LIB_PATH} is missing: the CUDA engine has not been built and there is no CPU fallback. "
                 "Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or custom_gymnasium_environments_b200._build.build_library()).")
+        if lib_path == LIB_PATH and is_stale() and not os.environ.get("BENG_ALLOW_STALE"):
+            raise RuntimeError(
+                f"{LIB_PATH} was built from different sources than the ones in csrc/ (or its .srchash is missing): "
+                "rebuild with `python -c 'import __graft_entry__ as g; g.build()'` so that what runs is what the tree "
+                "says (BENG_ALLOW_STALE=1 overrides).")
         lib = C.CDLL(lib_path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Dict, Discrete, batch_space
-from .vector import AUTORESET_MODES, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
 
 BUILDING_NAMES = ("farm", "lumberyard", "quarry", "house")
 BUILDER_STAT_NAMES = ("n_episodes", "sum_return", "sum_length", "wins")
@@ -199,7 +199,7 @@ class BatchedWorldBuilderEnv(_VectorEnvBase):
         self.closed = True
 
 
-class WorldBuilderEnv:
+class WorldBuilderEnv(_EnvBase):
     """Single-instance gym.Env surface of the reference (world_builder_env.py:10-247) on the CUDA engine: a 1-env
     BatchedWorldBuilderEnv with auto-reset disabled; numpy observations, Python numbers, the reference's info keys."""
 

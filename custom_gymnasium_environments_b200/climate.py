@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Dict, MultiBinary, batch_space
-from .vector import AUTORESET_MODES, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
 
 OBS_DIM = 9
 CLIMATE_STAT_NAMES = ("n_episodes", "sum_return", "sum_length")
@@ -203,7 +203,7 @@ class BatchedSmartClimateEnv(_VectorEnvBase):
         self.closed = True
 
 
-class SmartClimateEnv:
+class SmartClimateEnv(_EnvBase):
     """Single-instance gym.Env surface of the reference (env.py:10-128) on the CUDA engine: a 1-env
     BatchedSmartClimateEnv with auto-reset disabled; numpy observations, Python floats, the reference's info keys."""
 

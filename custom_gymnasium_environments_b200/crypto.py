@@ -22,7 +22,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Discrete, batch_space
-from .vector import AUTORESET_MODES, LazyInfos as _LazyInfos, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, LazyInfos as _LazyInfos, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
 
 HISTORY = 50
 OBS_DIM = 261
@@ -275,7 +275,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
         self.closed = True
 
 
-class CryptoTradingEnv:
+class CryptoTradingEnv(_EnvBase):
     """Single-instance gym.Env surface of the reference (crypto_trading_env.py:224-561) on the CUDA engine: a
     1-env BatchedCryptoTradingEnv with auto-reset disabled; numpy observations, Python floats, the reference's
     info keys (trade_info is rebuilt on the host from the cash/holdings deltas)."""

@@ -75,9 +75,11 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
                  : "l"(p));
     return r;
 }
+// (coherent, not .nc: under programmatic dependent launch the producer of the action tensor may still be running when
+// this grid becomes resident, and .nc data must be read-only for the whole lifetime of the grid)
 __device__ __forceinline__ long long ld_stream_s64(const long long *p) {
     long long r;
-    asm volatile("ld.global.nc.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
+    asm volatile("ld.global.L1::no_allocate.s64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
 

@@ -518,6 +518,7 @@ int launch(const Args &a, cudaStream_t stream) {
         return ownrow ? launch_one<TT, SS, IS_RESET, true>(a, c, stream)                    \
                       : launch_one<TT, SS, IS_RESET, false>(a, c, stream);
     BENG_CASE(256, 1) BENG_CASE(256, 2) BENG_CASE(128, 1) BENG_CASE(128, 2) BENG_CASE(128, 3) BENG_CASE(64, 1)
+    BENG_CASE(224, 1) BENG_CASE(192, 1) BENG_CASE(160, 1) BENG_CASE(96, 1)  /* non-power-of-two tiles (round-2 sweep) */
     BENG_CASE(64, 2) BENG_CASE(64, 3) BENG_CASE(64, 4) BENG_CASE(32, 1) BENG_CASE(32, 2) BENG_CASE(32, 4)
 #undef BENG_CASE
     return BENG_ERR_UNSUPPORTED;

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Discrete, batch_space
-from .vector import AUTORESET_MODES, LazyInfos, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, LazyInfos, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
 
 STAT_NAMES = ("n_episodes", "sum_return", "sum_length", "sum_score", "max_score")
 
@@ -288,7 +288,7 @@ class BatchedSnakeEnv(_VectorEnvBase):
         self.closed = True
 
 
-class SnakeEnvClassic:
+class SnakeEnvClassic(_EnvBase):
     """Single-instance gym.Env surface of the reference (snake_env.py:9-143) on the CUDA engine.
 
     A 1-env BatchedSnakeEnv with auto-reset DISABLED, i.e. exactly the reference class: numpy

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, MultiDiscrete, batch_space
-from .vector import AUTORESET_MODES, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
 
 # config.py:6-12,23
 DEFAULT_GRID_SIZE = (5, 5)
@@ -152,7 +152,7 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
             self._infos_cache = {"total_reward": self._total_reward, "reward64": self.reward64,
                                  "episode": {"r": self.ep_return, "l": self.ep_length}, "_episode": self.terminated}
         info = dict(self._infos_cache)
-        info["timestep"] = self._misc[0]     # low 16 bits; see current_timestep
+        info["timestep"] = self._misc[0] & 0xFFFF  # (the upper bits of the word are flags)
         info["num_vehicles"] = self._misc[1]
         return info
 
@@ -259,7 +259,7 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
         self.closed = True
 
 
-class TrafficManagementEnv:
+class TrafficManagementEnv(_EnvBase):
     """Single-instance gym.Env surface of the reference (environment.py:31-384) on the CUDA engine: a 1-env
     BatchedTrafficManagementEnv with auto-reset disabled; numpy observations, Python floats and the reference's
     info dict (timestep, num_vehicles, total_reward, metrics, intersection_states)."""

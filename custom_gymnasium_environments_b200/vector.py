@@ -21,6 +21,13 @@ except Exception:
         def close(self, **kwargs):
             self.closed = True
 
+try:  # pragma: no cover
+    from gymnasium import Env as _EnvBase  # type: ignore  (gym.make refuses entry points that are not gymnasium.Env)
+except Exception:
+    class _EnvBase:  # minimal stand-in for the single-instance facades
+        metadata = {}
+        render_mode = None
+
 AUTORESET_MODES = {"disabled": 0, "next_step": 1, "same_step": 2}
 
 

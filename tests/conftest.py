@@ -14,11 +14,12 @@ def pytest_configure(config):
 
 def pytest_sessionstart(session):
     """The in-tree libbeng.so normally travels with the repo snapshot.  If it is absent (a fresh checkout) compile it
-    once -- the same nvcc command as __graft_entry__.build() -- so that the tests exercise the CUDA library instead of
-    failing at import; compiling is not a fallback, the product still refuses to run without the library."""
+    once -- the same nvcc command as __graft_entry__.build() -- and recompile it when a source changed since it was built
+    (content hash, _build.is_stale), so that the tests exercise the CUDA library the tree describes instead of failing at
+    import or silently testing an old binary; compiling is not a fallback, the product still refuses to run without the library."""
     from custom_gymnasium_environments_b200 import _build, _lib
 
-    if not os.path.exists(_lib.LIB_PATH) and "BENG_LIB_PATH" not in os.environ:
+    if "BENG_LIB_PATH" not in os.environ and _build.is_stale():  # missing, or built from other sources than the tree's
         _build.build_library(force=True)
 
 

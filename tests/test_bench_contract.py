@@ -70,3 +70,29 @@ def test_registration_ids_match_the_reference(monkeypatch):
         assert hasattr(__import__(module, fromlist=[cls]), cls), env_id
     registration.register_all()
     assert len(calls) == 4  # nothing is registered twice
+
+
+def test_facades_are_gymnasium_envs_when_gymnasium_is_importable(tmp_path):
+    """gym.make() refuses entry points that do not inherit gymnasium.Env: with a gymnasium on the path the single-instance
+    facades must subclass its Env (and the batched classes its VectorEnv).  Checked in a subprocess with a stub package."""
+    pkg = tmp_path / "gymnasium"
+    (pkg / "vector").mkdir(parents=True)
+    (pkg / "envs").mkdir()
+    (pkg / "__init__.py").write_text("class Env:\n    metadata = {}\n    render_mode = None\n")
+    (pkg / "vector" / "__init__.py").write_text("class VectorEnv:\n    metadata = {}\n    closed = False\n")
+    (pkg / "envs" / "__init__.py").write_text("")
+    (pkg / "envs" / "registration.py").write_text(
+        "registry = {}\n"
+        "def register(id, entry_point, max_episode_steps=None, **kw):\n"
+        "    registry[id] = entry_point\n")
+    code = ("import gymnasium, gymnasium.vector, custom_gymnasium_environments_b200 as p\n"
+            "for c in (p.SnakeEnvClassic, p.CryptoTradingEnv, p.TrafficManagementEnv, p.SmartClimateEnv, p.WorldBuilderEnv):\n"
+            "    assert issubclass(c, gymnasium.Env), c\n"
+            "for c in (p.BatchedSnakeEnv, p.BatchedCryptoTradingEnv, p.BatchedTrafficManagementEnv):\n"
+            "    assert issubclass(c, gymnasium.vector.VectorEnv), c\n"
+            "from gymnasium.envs.registration import registry\n"
+            "assert 'snake_env_classic-v0' in registry and 'CryptoTrading-v0' in registry, registry\n"
+            "print('ok')\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                         env=dict(os.environ, PYTHONPATH=f"{tmp_path}{os.pathsep}{ROOT}"))
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
