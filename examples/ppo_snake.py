@@ -42,7 +42,9 @@ class SnakePolicy(nn.Module):
         self.v = nn.Linear(hidden, 1)
 
     def forward(self, obs_i8):
-        x = F.one_hot(obs_i8.long(), 3).permute(0, 3, 1, 2).to(torch.bfloat16)
+        # one-hot straight from the int8 grid (no int64 copy of the observation): channel c = (cell == c)
+        classes = torch.arange(3, dtype=torch.int8, device=obs_i8.device).view(1, 3, 1, 1)
+        x = (obs_i8.unsqueeze(1) == classes).to(torch.bfloat16)
         x = F.relu(self.c1(x))
         x = F.relu(self.c2(x))
         x = F.relu(self.fc(x.flatten(1)))
@@ -55,7 +57,7 @@ def timed(stream):
     return a, b
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=1 << 18, help="envs per GPU")
     ap.add_argument("--horizon", type=int, default=16)
@@ -63,8 +65,13 @@ def main():
     ap.add_argument("--minibatch", type=int, default=1 << 16)
     ap.add_argument("--fwd-chunk", type=int, default=1 << 17, help="envs per policy-forward chunk (bounds activations)")
     ap.add_argument("--lr", type=float, default=3e-4)
-    args = ap.parse_args()
+    ap.add_argument("--out", default=None, help="also write the JSON line to this file (rank 0)")
+    return ap.parse_args(argv)
 
+
+def run(args, record=None):
+    """One PPO run.  -> the result dict (rank 0; None elsewhere).  `record`: a list that receives, per iteration, clones
+    of (actions (T, n), observations (T + 1, n, G, G)) -- what tests/test_ppo_example_gpu.py replays through a second env."""
     rank, local_rank, world = init_process_group()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -140,6 +147,8 @@ def main():
             opt.step()
         b2.record(stream)
         torch.cuda.synchronize(dev)
+        if record is not None:
+            record.append((act_buf.clone(), obs_buf.clone()))
         obs_buf[0].copy_(obs_buf[T])
         if it > 0 or args.iters == 1:  # iteration 0 is warm-up (cudnn autotune, allocator)
             split["env_step_ms"] += sum(a.elapsed_time(b) for a, b in ev_env)
@@ -147,6 +156,7 @@ def main():
             split["update_ms"] += a2.elapsed_time(b2)
     wall = time.perf_counter() - t_wall
     stats = summarize(all_reduce_episode_stats(env.stats))
+    out = None
     if rank == 0:
         timed_iters = max(1, args.iters - 1) if args.iters > 1 else 1
         tot = sum(split.values())
@@ -157,8 +167,20 @@ def main():
                "env_steps_per_s_end_to_end": world * n * T * args.iters / wall,
                "env_steps_per_s_env_only": world * n * T * timed_iters / (split["env_step_ms"] * 1e-3),
                "episodes": stats, "loss": float(loss)}
-        print(json.dumps(out), flush=True)
-    if world > 1:
+    return out
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    out = run(args)
+    if out is not None:
+        line = json.dumps(out)
+        print(line, flush=True)
+        if args.out:
+            os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+            with open(args.out, "w") as f:
+                f.write(line + "\n")
+    if dist.is_available() and dist.is_initialized():
         dist.barrier()
         dist.destroy_process_group()
 
