@@ -617,10 +617,16 @@ def run_b200_arm(args):
     import torch
     import torch.distributed as dist
 
+    nccl_logs = None
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("NCCL_DEBUG_FILE"):
-        # NCCL's banner and communicator lines would precede the JSON line on stdout: send them to stderr instead,
-        # where whoever asked for them (the driver's rank check) still sees every "comm ... nranks N" line.
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+        # NCCL's banner and communicator lines would precede the JSON line on stdout.  Each rank logs to its own file
+        # (eight ranks writing to one stderr pipe garble each other's lines); rank 0 replays the version and
+        # "comm ... rank R nranks N" lines to stderr at the end, where whoever asked for them (the driver's rank check)
+        # sees them whole.  stdout carries the JSON line only.
+        nccl_logs = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(nccl_logs, exist_ok=True)
+        os.environ["NCCL_DEBUG_FILE"] = os.path.join(nccl_logs, "nccl.%h.%p.log")
+    t_start = time.time()
 
     import custom_gymnasium_environments_b200 as pkg
     from custom_gymnasium_environments_b200.dist import init_process_group
@@ -684,6 +690,17 @@ def run_b200_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if nccl_logs:
+        import glob
+
+        for path in sorted(glob.glob(os.path.join(nccl_logs, "nccl.*.log"))):
+            if os.path.getmtime(path) < t_start - 1:
+                continue
+            with open(path, errors="replace") as f:
+                for ln in f:
+                    if "nranks" in ln or "NCCL version" in ln:
+                        sys.stderr.write(ln)
+        sys.stderr.flush()
 
 
 def main():

@@ -166,7 +166,7 @@ def run(args, record=None):
                "share": {k: v / tot for k, v in split.items()},
                "env_steps_per_s_end_to_end": world * n * T * args.iters / wall,
                "env_steps_per_s_env_only": world * n * T * timed_iters / (split["env_step_ms"] * 1e-3),
-               "episodes": stats, "loss": float(loss)}
+               "episodes": stats, "loss": float(loss.detach())}
     return out
 
 
