@@ -126,7 +126,7 @@ class BatchedSmartClimateEnv(_VectorEnvBase):
     def _to_device(self, value, buf):
         if isinstance(value, torch.Tensor):
             if value.device == buf.device and value.dtype == buf.dtype and value.is_contiguous() \
-                    and value.numel() == buf.numel():
+                    and value.numel() == buf.numel() and value.data_ptr() % 16 == 0:  # (a misaligned view goes through buf)
                 return value
             buf.copy_(value.reshape(buf.shape), non_blocking=True)
             return buf

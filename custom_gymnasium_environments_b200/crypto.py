@@ -196,7 +196,7 @@ class BatchedCryptoTradingEnv(_VectorEnvBase):
         buf = self._actions
         if isinstance(actions, torch.Tensor):
             if actions.device == buf.device and actions.dtype == buf.dtype and actions.is_contiguous() \
-                    and actions.shape == buf.shape:
+                    and actions.shape == buf.shape and actions.data_ptr() % 16 == 0:
                 return actions
             buf.copy_(actions.reshape(buf.shape), non_blocking=True)
             return buf

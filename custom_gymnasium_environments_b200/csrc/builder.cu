@@ -295,6 +295,7 @@ int beng_builder_step(const beng_builder_params *p, const beng_builder_state *st
                       const beng_builder_io *io, int64_t n_envs, void *stream) {
     if (int rc = beng::check(p, st, io, n_envs)) return rc;
     if (!actions_dev || !io->reward || !io->terminated) return BENG_ERR_BAD_ARG;
+    if ((uintptr_t)actions_dev & 7) return BENG_ERR_BAD_ARG;  // 64-bit action loads (int64, or float32 pairs)
     if (n_envs == 0) return 0;
     beng::BArgs a{*p, *st, *io, (const long long *)actions_dev, nullptr, (long long)n_envs, 0};
     return beng::launch<false>(a, (cudaStream_t)stream);

@@ -243,8 +243,8 @@ int beng_climate_reset(const beng_climate_params *p, const beng_climate_state *s
 int beng_climate_step(const beng_climate_params *p, const beng_climate_state *st, const float *ac_temp_dev,
                       const int8_t *lights_dev, const beng_climate_io *io, int64_t n_envs, void *stream) {
     if (int rc = beng::check(p, st, io, n_envs)) return rc;
-    if (!ac_temp_dev || !lights_dev || !io->reward || !io->terminated || ((uintptr_t)lights_dev & 3))
-        return BENG_ERR_BAD_ARG;
+    if (!ac_temp_dev || !lights_dev || !io->reward || !io->terminated) return BENG_ERR_BAD_ARG;
+    if (((uintptr_t)lights_dev & 3) || ((uintptr_t)ac_temp_dev & 3)) return BENG_ERR_BAD_ARG;  // lights are read as one uint32 per env
     if (n_envs == 0) return 0;
     beng::KArgs a{*p, *st, *io, ac_temp_dev, lights_dev, nullptr, (long long)n_envs, 0};
     return beng::launch<false>(a, (cudaStream_t)stream);

@@ -1169,6 +1169,7 @@ int beng_crypto_step(const beng_crypto_params *p, const beng_crypto_state *st, c
                      const beng_crypto_io *io, int64_t n_envs, void *stream) {
     if (int rc = beng::check(p, st, io, n_envs)) return rc;
     if (!actions_dev || !io->reward || !io->terminated) return BENG_ERR_BAD_ARG;
+    if ((uintptr_t)actions_dev & 7) return BENG_ERR_BAD_ARG;  // 64-bit action loads (int64, or float32 pairs)
     if (n_envs == 0) return 0;
     beng::CArgs a{*p, *st, *io, actions_dev, nullptr, (long long)n_envs, beng_crypto_window_pitch(n_envs), 0};
     return beng::launch<false>(a, (cudaStream_t)stream);

@@ -583,6 +583,7 @@ int beng_snake_step(const beng_snake_params *p, const beng_snake_state *st, cons
                     const beng_snake_io *io, int64_t n_envs, void *stream) {
     if (int rc = beng::check_common(p, st, io, n_envs)) return rc;
     if (!actions_dev || !io->reward || !io->terminated) return BENG_ERR_BAD_ARG;
+    if ((uintptr_t)actions_dev & 7) return BENG_ERR_BAD_ARG;  // 64-bit action loads (int64, or float32 pairs)
     if (n_envs == 0) return 0;
     beng::Args a = beng::make_args(p, st, io, n_envs);
     a.actions = (const long long *)actions_dev;

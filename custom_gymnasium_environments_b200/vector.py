@@ -58,7 +58,7 @@ def as_device_actions(actions, buf: torch.Tensor) -> torch.Tensor:
     """Return a contiguous int64 CUDA tensor shaped like `buf` holding `actions` (zero-copy when possible)."""
     if isinstance(actions, torch.Tensor):
         if actions.device == buf.device and actions.dtype == torch.int64 and actions.is_contiguous() \
-                and actions.shape == buf.shape:
+                and actions.shape == buf.shape and actions.data_ptr() % 16 == 0:  # (a misaligned view goes through buf)
             return actions
         buf.copy_(actions.reshape(buf.shape), non_blocking=True)
         return buf

@@ -311,3 +311,32 @@ def test_single_env_facade_matches_reference_anchor(pkg, golden):
         env.step(4)
     with pytest.raises(ValueError):
         env.step(1.0)
+
+
+def test_render_rgb_array_and_misaligned_action_views(pkg):
+    """render(): the reference's 3-colour LUT (snake_env.py:175-188) over the current observation.  A contiguous action
+    view that starts at an odd element (8-byte but not 16-byte aligned storage offset) must take the staging-buffer path
+    and give the same step as an aligned copy; through the C ABI a misaligned pointer is an argument error, not a fault."""
+    import ctypes as C
+
+    n = 64
+    env = pkg.BatchedSnakeEnv(n, device=DEV, seed=2)
+    env.render_mode = "rgb_array"
+    obs, _ = env.reset()
+    img = env.render()
+    assert img.shape == (n, 400, 400, 3) and img.dtype == np.uint8
+    cell = img[:, ::20, ::20]  # one pixel per grid cell
+    o = obs.cpu().numpy()
+    assert np.array_equal(cell[..., 1] == 255, o == 1) and np.array_equal(cell[..., 0] == 255, o == 2)
+    twin = pkg.BatchedSnakeEnv(n, device=DEV, seed=2)
+    twin.reset()
+    big = torch.randint(0, 4, (n + 1,), device=DEV)
+    view = big[1:]  # data_ptr() % 16 == 8
+    assert view.is_contiguous() and view.data_ptr() % 16 != 0
+    a_obs, a_rew, *_ = env.step(view)
+    b_obs, b_rew, *_ = twin.step(view.clone())
+    assert torch.equal(a_obs, b_obs) and torch.equal(a_rew, b_rew)
+    lib = pkg._lib.load()
+    rc = lib.beng_snake_step(C.byref(env.params), C.byref(env._state), view.data_ptr() + 4, C.byref(env._ios_full[0]), n,
+                             torch.cuda.current_stream().cuda_stream)
+    assert rc == -1  # BENG_ERR_BAD_ARG
