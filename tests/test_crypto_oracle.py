@@ -121,3 +121,57 @@ def test_c_oracle_matches_live_reference():
                 assert info["portfolio_value"] == one.portfolio_value[0]
     finally:
         mod.np = real_np
+
+
+def macd_weight_vectors(hist=50):
+    """The two constant vectors of csrc/crypto.cu::make_macd_weights, restated in numpy: run the reference's recurrences
+    (`_ema`, crypto_trading_env.py:108-119; the EMA-of-MACD-history of `macd`, :94-100) on the coefficient vectors of the
+    closes instead of on the closes.  -> (wm, wg) with MACD line = wm . closes, signal line = wg . closes."""
+    mf, ms, mg = 2.0 / 13.0, 2.0 / 27.0, 2.0 / 10.0
+    wf, ws, sg = np.zeros(hist), np.zeros(hist), np.zeros(hist)
+    wf[0] = ws[0] = 1.0
+    for t in range(1, hist):
+        wf[:t] *= 1.0 - mf
+        ws[:t] *= 1.0 - ms
+        wf[t], ws[t] = mf, ms
+        if t == 25:
+            sg = wf - ws
+        elif t > 25:
+            sg = (wf - ws) * mg + sg * (1.0 - mg)
+    return wf - ws, sg
+
+
+def test_macd_is_a_pair_of_dot_products():
+    """What the CUDA step kernel relies on: an EMA seeded with prices[0] is linear in the window, so
+    MACD line and signal line are dot products of the 50 closes with constant weights that sum to zero -- taken with
+    (close - newest close), as the kernel does.  Checked against the oracle's serial float64 recurrences (features 254..256
+    = macd / range, signal / range, histogram / range) far inside the 1e-5 observation tolerance."""
+    wm, wg = macd_weight_vectors()
+    assert abs(wm.sum()) < 1e-15 and abs(wg.sum()) < 1e-15
+    n = 512
+    orc = CryptoOracle(n, seed=5)
+    orc.reset()
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for t in range(120):
+        obs, *_ = orc.step(rng.integers(0, 5, n))
+        closes = orc.state(with_candles=True)["candles"][:, :, 3]          # (n, 50) float64, oldest first
+        d = closes - closes[:, -1:]
+        span = closes.max(axis=1) - closes.min(axis=1)
+        ok = span > 0
+        feats = np.stack([d @ wm, d @ wg, d @ wm - d @ wg], axis=1)[ok] / span[ok, None]
+        ref = obs[ok, 254:257].astype(np.float64)
+        worst = max(worst, float(np.max(np.abs(feats - ref) / (1e-6 + 1e-5 * np.abs(ref)))))
+    assert worst < 0.05, worst  # (the float32 rounding of the oracle's observation is the only difference)
+
+
+def test_staged_reference_copies_are_byte_identical():
+    """oracle/make_ref.py: the files bench.py's CPU arm and the live-reference tests run on the GPU box are byte-for-byte
+    the reference's (sha256 manifest; compared with /root/reference itself when it is present)."""
+    from oracle import make_ref
+
+    if not make_ref.source_available() and not os.path.exists(os.path.join(make_ref.DEST, "MANIFEST.json")):
+        pytest.skip("neither /root/reference nor oracle/_ref is present")
+    if make_ref.source_available():
+        make_ref.stage(verbose=False)
+    assert make_ref.check()
