@@ -164,6 +164,30 @@ __device__ __noinline__ WarmupResult warmup_window(double *close_arr, float4 *oh
 // repeat (one extra pass per regime change: 0.5 on average).
 // `stage` is 100 doubles of warp-private shared memory, element d at stage[(d >> 4) * stage_stride + (d & 15)].
 // All 32 lanes call this with identical arguments.  Bit-identical to warmup_window() (tests: sparse-reset rollouts).
+// 20 consecutive words of an env's stream, starting at the Philox block that holds draw `c`: five blocks computed up
+// front, no "is my block cached?" branch per draw (lanes of a warp sit at different alignments, so the lazy EnvStream
+// evaluated Philox up to once per draw: ~30 times per candle instead of 5).  Same draw -> value maps as EnvStream.
+struct WordWindow {
+    uint32_t w[20];  // (indexed by a per-lane position: lives in local memory; this is the rare reset path)
+    uint32_t pos;
+    __device__ __forceinline__ WordWindow(uint64_t seed, uint64_t env, uint32_t c) : pos(c & 3u) {
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const Philox4 r = philox4x32_10((c >> 2) + b, (uint32_t)env, (uint32_t)(env >> 32), BENG_STREAM_ENV,
+                                            (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) w[4 * b + q] = r.v[q];
+        }
+    }
+    __device__ __forceinline__ uint32_t u32() { return w[pos++]; }
+    __device__ __forceinline__ int randint(int a, int b) { return a + (int)__umulhi(u32(), (uint32_t)(b - a + 1)); }
+    __device__ __forceinline__ double random53() {
+        const uint32_t a = u32() >> 5, b = u32() >> 6;
+        return ((double)a * 67108864.0 + (double)b) * (1.0 / 9007199254740992.0);
+    }
+    __device__ __forceinline__ double uniform(double a, double b) { return a + (b - a) * random53(); }
+};
+
 __device__ __noinline__ WarmupResult coop_warmup_window(double *close_arr, float4 *ohlv_arr, long long n, long long env,
                                                         int head, beng_crypto_params p, Market m, uint64_t gid,
                                                         uint32_t ctr, double *stage, int stage_stride) {
@@ -179,7 +203,7 @@ __device__ __noinline__ WarmupResult coop_warmup_window(double *close_arr, float
         for (int h = 0; h < 2; ++h) {
             const int k = lane + 32 * h;
             if (k < HIST && k > resolved) {  // (first pass: every candle; later: the ones behind the new change)
-                EnvStream r(p.seed, gid, BENG_STREAM_ENV, ctr + 14u * (uint32_t)k + 3u * (uint32_t)changes);
+                WordWindow r(p.seed, gid, ctr + 14u * (uint32_t)k + 3u * (uint32_t)changes);
                 volume[h] = r.uniform(0.5, 2.0);
                 fires[h] = r.random53() < 0.01;
                 if (fires[h]) {
@@ -211,7 +235,9 @@ __device__ __noinline__ WarmupResult coop_warmup_window(double *close_arr, float
         }
     }
     __syncwarp();
-    double price = 50000.0;
+    // The serial state chain, run redundantly by every lane (nothing to broadcast, nothing to synchronise inside the
+    // loop); a lane keeps the closes of its own two candles as they go by.
+    double price = 50000.0, c0 = 0.0, c1 = 0.0;
 #pragma unroll 1
     for (int k = 0; k < HIST; ++k) {
         if ((fired >> k) & 1ull) {  // warp-uniform
@@ -221,22 +247,21 @@ __device__ __noinline__ WarmupResult coop_warmup_window(double *close_arr, float
             apply_regime(m, pk, r);
         }
         price = price_update(p, m, price, at(k), at(HIST + k));
-        __syncwarp();
-        if (lane == 0) at(k) = price;  // z[k] is consumed: its slot now carries the close
+        if (k == lane) c0 = price;
+        if (k == lane + 32) c1 = price;
     }
-    __syncwarp();
     const int oldest = head + 1 == HIST ? 0 : head + 1;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int k = lane + 32 * h;
         if (k < HIST) {
-            const double c = at(k);
+            const double c = h ? c1 : c0;
             int slot = oldest + k;
             slot = slot >= HIST ? slot - HIST : slot;
             store_candle(close_arr, ohlv_arr, n, env, slot, c * uo[h], c * uh[h], c * ul[h], c, volume[h]);
         }
     }
-    __syncwarp();
+    __syncwarp();  // (the stage may be reused, and the caller's lanes read these stores after their own __syncwarp)
     return WarmupResult{m, ctr + 14u * HIST + 3u * (uint32_t)changes, price};
 }
 
