@@ -43,6 +43,7 @@ struct TArgs {
     const uint8_t *mask;
     long long n;
     int ni, first_call;
+    uint32_t inv_cols;  // ceil(2^16 / grid_cols): (start * inv_cols) >> 16 == start / grid_cols for start < 25
 };
 
 // NumPy's pairwise summation (np.var in _calculate_reward, n <= 128) over f(0..n-1), without materialising the array
@@ -111,23 +112,186 @@ __device__ __forceinline__ void spawn_route(const TArgs &a, Stream &rng, int &st
     const int rows = a.p.grid_rows, cols = a.p.grid_cols;
     start = rng.randint(0, a.ni - 1);
     const int route_length = rng.randint(2, a.ni < 5 ? a.ni : 5);
-    int row = start / cols, col = start % cols;
+    const int row0 = (int)(((uint32_t)start * a.inv_cols) >> 16), col0 = start - row0 * cols;  // start / cols, start % cols
+    int row = row0, col = col0;
     dir = NORTH;
     for (int h = 1; h < route_length; ++h) {
         // neighbours in the reference's order N, S, W, E (utils.py:206), bounds of the FULL grid (ids up to rows*cols-1)
-        const bool hn = row > 0, hs = row + 1 < rows, hw = col > 0, he = col + 1 < cols;
-        const int cnt = hn + hs + hw + he;
-        int pick = rng.randint(0, cnt - 1);  // random.choice(neighbors)
-        int d;
-        if (hn && pick-- == 0) d = NORTH;
-        else if (hs && pick-- == 0) d = SOUTH;
-        else if (hw && pick-- == 0) d = WEST;
-        else d = EAST;
-        row += (d == SOUTH) - (d == NORTH);
-        col += (d == EAST) - (d == WEST);
-        if (h == 1) dir = d;
+        uint32_t m = (uint32_t)(row > 0) | ((uint32_t)(row + 1 < rows) << 1) | ((uint32_t)(col > 0) << 2) |
+                     ((uint32_t)(col + 1 < cols) << 3);
+        const int pick = rng.randint(0, __popc(m) - 1);  // random.choice(neighbors)
+        m = pick > 0 ? m & (m - 1) : m;                   // drop the `pick` lowest candidates
+        m = pick > 1 ? m & (m - 1) : m;
+        m = pick > 2 ? m & (m - 1) : m;
+        const int c = __ffs((int)m) - 1;                  // 0 N, 1 S, 2 W, 3 E
+        row += (c == 1) - (c == 0);
+        col += (c == 3) - (c == 2);
+        if (h == 1) dir = (0x1320 >> (c * 4)) & 3;        // -> Direction ids NORTH 0, EAST 1, SOUTH 2, WEST 3
     }
-    loopback = (row * cols + col) == start;
+    loopback = row == row0 && col == col0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-intersection building blocks shared by the kernels below.  Written branch-free on the hot path: the profile of
+// the first formulation showed ~500 warp-instructions per intersection, a third of them in divergent `if (cnt)` /
+// `if (wipe)` regions executed with 2-4 live lanes, and another fifth in IEEE float divisions (the mean waiting time
+// of every queue) that mostly took the slow path because the numerator was 0.
+struct IxState {
+    uint32_t l0, qm[4];  // light word, queue meta words as loaded
+    int passed, wait, qw[4];
+};
+
+__device__ __forceinline__ void load_ix(const TArgs &a, uint32_t i, uint32_t un, uint32_t e32, bool ok, IxState &s) {
+    s.l0 = 0; s.passed = 0; s.wait = 0;
+#pragma unroll
+    for (int d = 0; d < 4; ++d) { s.qm[d] = 0; s.qw[d] = 0; }
+    if (ok) {
+        s.l0 = a.st.light[i * un + e32];
+        s.passed = a.st.passed[i * un + e32];
+        s.wait = a.st.waiting[i * un + e32];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            s.qm[d] = a.st.qmeta[(i * 4 + d) * un + e32];
+            s.qw[d] = a.st.qwait[(i * 4 + d) * un + e32];
+        }
+    }
+}
+
+// _apply_actions (:205-220) + TrafficLight.update (utils.py:79-97) of one light; returns whether the light turned green
+// and therefore draws randint(5, 30) (the caller places that draw in the env's stream, in light-id order).
+__device__ __forceinline__ bool light_update(uint32_t l0, long long act, bool step, int &ph, int &tm) {
+    ph = (int)(l0 & 0xFF);
+    tm = (int)(l0 >> 8);
+    const bool to_ns = step && act == 1 && ph != NS_GREEN;  // set_phase: MIN_PHASE_DURATION
+    const bool to_ew = step && act == 2 && ph != EW_GREEN;
+    ph = to_ns ? (int)NS_GREEN : to_ew ? (int)EW_GREEN : ph;
+    tm = (to_ns || to_ew) ? 5 : tm;
+    tm -= step ? 1 : 0;
+    const bool adv = step && tm <= 0;                        // _advance_phase
+    ph = adv ? (ph + 1) & 3 : ph;
+    const bool yellow = adv && (ph & 1);
+    tm = yellow ? 3 : tm;                                    // YELLOW_DURATION
+    return adv && !(ph & 1);
+}
+
+// 1 / cnt for the mean waiting time of a queue: (float)((double)qw * rcp[cnt]) equals the reference's
+// float32(qw / cnt) wherever the quotient is below 2^24 (a float32 rounding breakpoint is at least 2^-33 away from
+// qw / cnt in relative terms when cnt <= 255, the product is within 2^-52), and both are clamped to 100 above that.
+// rcp[0] = 0: an empty queue reports 0.  The table is a compile-time constant (IEEE division in the host compiler),
+// staged into shared memory by every CTA.
+struct RcpTable {
+    double v[256];
+    constexpr RcpTable() : v{} {
+        for (int i = 1; i < 256; ++i) v[i] = 1.0 / (double)i;
+    }
+};
+__device__ const RcpTable g_rcp_table{};
+
+__device__ __forceinline__ void fill_rcp_table(double *rcp, int tid, int nthreads) {
+    for (int i = tid; i < 256; i += nthreads) rcp[i] = g_rcp_table.v[i];
+}
+
+// Correctly rounded x / B for a compile-time B without the division subroutine (two of these sit on the env's serial
+// chain): y = RN(1 / B), q = RN(x * y), r = x - B * q exactly (FMA), result RN(q + r * y) -- Markstein's final
+// iteration, which returns the correctly rounded quotient when y is the correctly rounded reciprocal and q is within
+// an ulp of x / B.  (tests/test_traffic_oracle.py checks the sequence against x / 9 on CPU doubles.)
+template <int B>
+__device__ __forceinline__ double div_const(double x) {
+    constexpr double y = 1.0 / (double)B;
+    const double q = x * y;
+    const double r = fma(-(double)B, q, x);
+    return fma(r, y, q);
+}
+
+struct IxOut {
+    int pas, wt, qsum, left;
+};
+
+// _process_intersections (:271-281, utils.py:141-163), _remove_completed_vehicles (:283-285), the state write-back
+// (only words that changed) and the per-intersection features of the observation (:313-363) for intersection i of one
+// env.  `spq` = 4 * intersection + direction of the vehicle spawned this step (-1: none), `wipe`: the env is being
+// reset (fresh TrafficLight, empty queues, zero counters) -- the totals returned are those BEFORE the wipe, which is
+// what the reward of a same-step auto-reset is computed from.
+__device__ __forceinline__ IxOut process_ix(const TArgs &a, int NI, int i, uint32_t un, uint32_t e32, const IxState &s,
+                                            int ph, int tm, bool stepping, bool wipe, int spq, int sp_lb, float *row,
+                                            const double *rcp) {
+    const bool go_ns = stepping && ph == NS_GREEN, go_ew = stepping && ph == EW_GREEN;      // can_pass
+    const bool wait_ns = stepping && ph != NS_GREEN, wait_ew = stepping && ph != EW_GREEN;
+    int pas = s.passed, wt = s.wait, qsum = 0, left = 0;
+    uint32_t qm_new[4];
+    int qw_new[4];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {  // N, E, S, W
+        const bool go = (d & 1) ? go_ew : go_ns, wait = (d & 1) ? wait_ew : wait_ns;
+        const uint32_t qi = (uint32_t)(i * 4 + d) * un + e32;
+        int cnt = (int)(s.qm[d] & 0xFF), lb = (int)(s.qm[d] >> 8);
+        const int hit = spq == i * 4 + d;  // add_vehicle_to_queue, waiting_time 0
+        cnt += hit;
+        lb += hit & sp_lb;
+        pas += go ? cnt : 0;               // the whole queue proceeds; loop-back vehicles leave self.vehicles
+        left += go ? lb : 0;
+        wt += wait ? cnt : 0;              // every queued vehicle waits one more step
+        int qw = s.qw[d] + (wait ? cnt : 0);
+        cnt = go ? 0 : cnt;
+        lb = go ? 0 : lb;
+        qw = go ? 0 : qw;
+        qsum += cnt;
+        qm_new[d] = (uint32_t)cnt | ((uint32_t)lb << 8);
+        qw_new[d] = qw;
+        if (qm_new[d] != s.qm[d]) a.st.qmeta[qi] = (uint16_t)qm_new[d];
+        if (qw != s.qw[d]) a.st.qwait[qi] = qw;
+        row[NI * 4 + i * 4 + d] = (float)min(cnt, 20);                            // MAX_QUEUE_LENGTH
+        row[NI * 8 + i * 4 + d] = fminf((float)((double)qw * rcp[cnt]), 100.0f);   // mean waiting time, <= 100
+    }
+    const uint32_t nl = (uint32_t)ph | ((uint32_t)tm << 8);
+    if (nl != s.l0) a.st.light[(uint32_t)i * un + e32] = (uint16_t)nl;
+    if (pas != s.passed) a.st.passed[(uint32_t)i * un + e32] = pas;
+    if (wt != s.wait) a.st.waiting[(uint32_t)i * un + e32] = wt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) row[i * 4 + q] = (ph == q) ? 1.0f : 0.0f;
+    row[NI * 12 + i * 2] = (float)pas;
+    row[NI * 12 + i * 2 + 1] = (float)min(wt, 1000);
+    if (wipe) {  // rare (episode boundaries): zero whatever the step left non-zero, observation of a fresh env
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const uint32_t qi = (uint32_t)(i * 4 + d) * un + e32;
+            if (qm_new[d]) a.st.qmeta[qi] = 0;
+            if (qw_new[d]) a.st.qwait[qi] = 0;
+            row[NI * 4 + i * 4 + d] = 0.0f;
+            row[NI * 8 + i * 4 + d] = 0.0f;
+        }
+        if (nl != NS_GREEN) a.st.light[(uint32_t)i * un + e32] = NS_GREEN;
+        if (pas) a.st.passed[(uint32_t)i * un + e32] = 0;
+        if (wt) a.st.waiting[(uint32_t)i * un + e32] = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) row[i * 4 + q] = q == NS_GREEN ? 1.0f : 0.0f;
+        row[NI * 12 + i * 2] = 0.0f;
+        row[NI * 12 + i * 2 + 1] = 0.0f;
+    }
+    return IxOut{pas, wt, qsum, left};
+}
+
+// The three float32 ratios of the global metrics.  (float)((double)a / (double)b) for non-negative integers; a == 0
+// short-cuts the IEEE division's slow path.
+__device__ __forceinline__ float ratio0_f32(long long a, long long b) { return a == 0 ? 0.0f : ratio_f32(a, b); }
+
+// _calculate_reward (:287-311): CUMULATIVE counters, float64, the reference's order of additions; q[i * stride] is the
+// queue total of intersection i (np.var: population variance over NumPy's pairwise sums).
+template <int NI_T>
+__device__ __forceinline__ double step_reward(int tot_passed, int tot_wait, int tot_queue, const int32_t *q, int stride,
+                                              int NI) {
+    double rew = 0.0;
+    rew += (double)tot_passed * 1.0;
+    rew += (double)tot_wait * -0.1;
+    rew += (double)tot_queue * -0.05;
+    if (NI > 1) {
+        const double sum = np_sum_fn([&](int i) { return (double)q[i * stride]; }, NI);
+        const double mean = NI_T ? div_const<NI_T ? NI_T : 1>(sum) : sum / (double)NI;
+        const double ssq = np_sum_fn([&](int i) { const double dq = (double)q[i * stride] - mean; return dq * dq; }, NI);
+        const double var = NI_T ? div_const<NI_T ? NI_T : 1>(ssq) : ssq / (double)NI;
+        rew += 0.5 / (1 + var);
+    }
+    return rew;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -145,16 +309,18 @@ __device__ __forceinline__ void spawn_route(const TArgs &a, Stream &rng, int &st
 //   barrier 3: per-intersection passed / waiting / queue totals -> reward (env warp), global metrics (warp 0)
 //   barrier 4: observation tile complete -> one bulk asynchronous copy per CTA
 // Every intersection warp waits for the env warp between barriers 1-2 and 3-4, so the env warp's code there is kept
-// short: its Philox blocks are computed ahead of barrier 1 (CachedStream), the global metrics are warp 0's.
+// short: its Philox blocks are computed ahead of barrier 1 (CachedStream), the global metrics are warp 0's, the two
+// float64 divisions by NI of the variance are FMA sequences instead of the division subroutine (div_const).
 constexpr int WPI_E = 32;  // envs per CTA
 
 template <int NI_T, int IPW, int MAXREG, bool IS_RESET>
-__global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
+__global__ void __maxnreg__(MAXREG) traffic_step_kernel(const TArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int NI = NI_T ? NI_T : a.ni;
     const int NW = (NI + IPW - 1) / IPW;  // intersection warps; warp NW is the env warp
     const int OD = NI * 14 + 4;
-    float *tile = reinterpret_cast<float *>(smem_raw);                       // [32][OD]
+    double *s_rcp = reinterpret_cast<double *>(smem_raw);                      // [256]
+    float *tile = reinterpret_cast<float *>(s_rcp + 256);                     // [32][OD]
     int32_t *s_part = reinterpret_cast<int32_t *>(tile + WPI_E * OD);         // [4][NI][32]
     int32_t *s_spawn = s_part + 4 * NI * WPI_E;                               // [32]
     uint32_t *s_phx = reinterpret_cast<uint32_t *>(s_spawn + WPI_E);          // [SPEC_BLOCKS*4][32]
@@ -164,15 +330,13 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
     const long long first = (long long)blockIdx.x * WPI_E;
     const long long env = first + lane;
     const bool active = env < n;
-    // element offsets fit 32 bits (check() refuses n * ni * 4 >= 2^32): one IMAD.WIDE per address instead of 64-bit chains
     const uint32_t un = (uint32_t)n, e32 = (uint32_t)env;
     float *row = tile + lane * OD;
-    // the two roles run different code between the same CTA-wide barriers (arrival is counted per warp)
     auto cta_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"r"((NW + 1) * 32) : "memory"); };
+    fill_rcp_table(s_rcp, threadIdx.x, (NW + 1) * 32);
     pdl_launch_dependents();
     pdl_wait();
 
-    // env header, read by every warp of the CTA (same 128-byte lines: L1 hits after the first)
     uint32_t m0 = 0, ctr = 0;
     bool selected = true;
     if (active) {
@@ -183,38 +347,28 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
     int timestep = m0 & 0xFFFF;
     uint32_t flags = m0 >> 16;
     const bool do_reset =
-        IS_RESET ? selected : (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & TFLAG_NEEDS_RESET));
+        active && (IS_RESET ? selected : (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & TFLAG_NEEDS_RESET)));
     if (IS_RESET && selected && a.first_call) ctr = 0;
     const bool stepping = !IS_RESET && !do_reset && active;
     if (stepping) timestep = min(timestep + 1, 65535);                                  // :170
     const bool term = stepping && timestep >= a.p.max_timesteps;                        // :196, reported as terminated
     const bool ended = term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED;
     const bool same_step = ended && a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP;
+    const bool wipe = do_reset || same_step;
 
     if (w < NW) {
         // ================= intersection warp: intersections w*IPW .. w*IPW+IPW-1 of 32 envs =================
         const int i0 = w * IPW;
-        // ---- phase A: loads; _apply_actions (:205-220) + TrafficLight.update (utils.py:79-97)
-        uint32_t l0[IPW], qm0[IPW][4];
-        int passed[IPW], wait[IPW], qw0[IPW][4], phase[IPW], timer[IPW];
+        IxState s[IPW];
         long long act[IPW];
+        int phase[IPW], timer[IPW];
 #pragma unroll
         for (int k = 0; k < IPW; ++k) {
             const int i = i0 + k;
-            l0[k] = 0; passed[k] = 0; wait[k] = 0; act[k] = 0;
-#pragma unroll
-            for (int d = 0; d < 4; ++d) { qm0[k][d] = 0; qw0[k][d] = 0; }
-            if (active && i < NI) {
-                l0[k] = a.st.light[(uint32_t)i * un + e32];
-                passed[k] = a.st.passed[(uint32_t)i * un + e32];
-                wait[k] = a.st.waiting[(uint32_t)i * un + e32];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    qm0[k][d] = a.st.qmeta[(uint32_t)(i * 4 + d) * un + e32];
-                    qw0[k][d] = a.st.qwait[(uint32_t)(i * 4 + d) * un + e32];
-                }
-                if constexpr (!IS_RESET) act[k] = a.actions[e32 * (uint32_t)NI + (uint32_t)i];
-            }
+            load_ix(a, (uint32_t)i, un, e32, active && i < NI, s[k]);
+            act[k] = 0;
+            if constexpr (!IS_RESET)
+                if (active && i < NI) act[k] = a.actions[e32 * (uint32_t)NI + (uint32_t)i];
         }
         int spawn = -1;
         if constexpr (!IS_RESET) {
@@ -222,20 +376,7 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
 #pragma unroll
             for (int k = 0; k < IPW; ++k) {
                 const int i = i0 + k;
-                int ph = l0[k] & 0xFF, tm = (int)(l0[k] >> 8);
-                need[k] = false;
-                if (stepping && i < NI) {
-                    if (act[k] == 1 && ph != NS_GREEN) { ph = NS_GREEN; tm = 5; }        // set_phase: MIN_PHASE_DURATION
-                    else if (act[k] == 2 && ph != EW_GREEN) { ph = EW_GREEN; tm = 5; }
-                    tm -= 1;
-                    if (tm <= 0) {                                                      // _advance_phase
-                        ph = (ph + 1) & 3;
-                        if (ph & 1) tm = 3;                                             // YELLOW_DURATION
-                        else need[k] = true;                                            // randint(5, 30), after barrier 1
-                    }
-                }
-                phase[k] = ph;
-                timer[k] = tm;
+                need[k] = light_update(s[k].l0, act[k], stepping && i < NI, phase[k], timer[k]);
                 const unsigned nb = __ballot_sync(0xFFFFFFFFu, need[k]);
                 if (lane == 0 && i < NI) s_need[i] = nb;
             }
@@ -253,91 +394,37 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
             spawn = s_spawn[lane];
         } else {
 #pragma unroll
-            for (int k = 0; k < IPW; ++k) { phase[k] = l0[k] & 0xFF; timer[k] = (int)(l0[k] >> 8); }
+            for (int k = 0; k < IPW; ++k) { phase[k] = s[k].l0 & 0xFF; timer[k] = (int)(s[k].l0 >> 8); }
+            cta_barrier();  // the reciprocal table is complete
         }
-
-        // ---- phase B: _process_intersections (:271-281, utils.py:141-163), _remove_completed_vehicles (:283-285)
-        // and the per-intersection features of the observation (:313-363)
-        if (active) {
-            const int sp_i = spawn & 0xFF, sp_d = (spawn >> 8) & 0xFF, sp_lb = (spawn >> 16) & 0xFF;
-            const bool wipe = do_reset || same_step;  // fresh TrafficLight (NS_GREEN, timer 0), empty queues, zero counters
+        const int spq = spawn >= 0 ? (spawn & 0xFF) * 4 + ((spawn >> 8) & 0xFF) : -1, sp_lb = (spawn >> 16) & 1;
 #pragma unroll
-            for (int k = 0; k < IPW; ++k) {
-                const int i = i0 + k;
-                if (i >= NI) break;
-                const bool sp_here = spawn >= 0 && sp_i == i;
-                int ph = phase[k], tm = timer[k], pas = passed[k], wt = wait[k];
-                if (do_reset) { ph = NS_GREEN; tm = 0; pas = 0; wt = 0; }
-                int qsum = 0, left = 0;
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const uint32_t qi = (uint32_t)(i * 4 + d) * un + e32;
-                    int cnt = 0, lb = 0, qw = 0;
-                    if (!do_reset) {
-                        cnt = qm0[k][d] & 0xFF;
-                        lb = qm0[k][d] >> 8;
-                        qw = qw0[k][d];
-                        if (stepping) {
-                            if (sp_here && d == sp_d) { cnt += 1; lb += sp_lb; }  // add_vehicle_to_queue, waiting_time 0
-                            if (cnt) {
-                                const bool green = (ph == NS_GREEN && (d == NORTH || d == SOUTH)) ||
-                                                   (ph == EW_GREEN && (d == EAST || d == WEST));  // can_pass
-                                if (green) {  // the whole queue proceeds; loop-back vehicles leave self.vehicles
-                                    pas += cnt;
-                                    left += lb;
-                                    cnt = 0; lb = 0; qw = 0;
-                                } else {      // every queued vehicle waits one more step
-                                    qw += cnt;
-                                    wt += cnt;
-                                }
-                            }
-                        }
-                    }
-                    qsum += cnt;
-                    if (wipe) {
-                        if (qm0[k][d]) a.st.qmeta[qi] = 0;
-                        if (qw0[k][d]) a.st.qwait[qi] = 0;
-                        cnt = 0; qw = 0;
-                    } else if (stepping) {
-                        const uint32_t qm = (uint32_t)cnt | ((uint32_t)lb << 8);
-                        if (qm != qm0[k][d]) a.st.qmeta[qi] = (uint16_t)qm;
-                        if (qw != qw0[k][d]) a.st.qwait[qi] = qw;
-                    }
-                    row[NI * 4 + i * 4 + d] = (float)min(cnt, 20);                            // MAX_QUEUE_LENGTH
-                    row[NI * 8 + i * 4 + d] = cnt ? fminf(ratio_f32(qw, cnt), 100.0f) : 0.0f;   // mean waiting time, <= 100
-                }
-                s_part[(0 * NI + i) * WPI_E + lane] = pas;
-                s_part[(1 * NI + i) * WPI_E + lane] = wt;
-                s_part[(2 * NI + i) * WPI_E + lane] = qsum;
-                s_part[(3 * NI + i) * WPI_E + lane] = left;
-                uint32_t nl = (uint32_t)ph | ((uint32_t)tm << 8);
-                if (wipe) { nl = NS_GREEN; pas = 0; wt = 0; ph = NS_GREEN; }
-                if (nl != l0[k]) a.st.light[(uint32_t)i * un + e32] = (uint16_t)nl;
-                if (pas != passed[k]) a.st.passed[(uint32_t)i * un + e32] = pas;
-                if (wt != wait[k]) a.st.waiting[(uint32_t)i * un + e32] = wt;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) row[i * 4 + q] = (ph == q) ? 1.0f : 0.0f;
-                row[NI * 12 + i * 2] = (float)pas;
-                row[NI * 12 + i * 2 + 1] = (float)min(wt, 1000);
-            }
+        for (int k = 0; k < IPW; ++k) {
+            const int i = i0 + k;
+            if (i >= NI) break;
+            const IxOut o = process_ix(a, NI, i, un, e32, s[k], phase[k], timer[k], stepping, wipe, spq, sp_lb, row, s_rcp);
+            s_part[(0 * NI + i) * WPI_E + lane] = o.pas;
+            s_part[(1 * NI + i) * WPI_E + lane] = o.wt;
+            s_part[(2 * NI + i) * WPI_E + lane] = o.qsum;
+            s_part[(3 * NI + i) * WPI_E + lane] = o.left;
         }
         cta_barrier();  // barrier 3
         if (w == 0 && active) {
             // global metrics (utils.py:251-267, environment.py:352-361), off the env warp's critical path
             int tot_passed = 0, tot_wait = 0, tot_queue = 0;
-            if (!same_step) {
+            if (!wipe) {
                 for (int j = 0; j < NI; ++j) {
                     tot_passed += s_part[(0 * NI + j) * WPI_E + lane];
                     tot_wait += s_part[(1 * NI + j) * WPI_E + lane];
                     tot_queue += s_part[(2 * NI + j) * WPI_E + lane];
                 }
             }
-            row[NI * 14 + 1] = fminf(ratio_f32(tot_wait, tot_passed > 1 ? tot_passed : 1), 100.0f);
-            row[NI * 14 + 2] = fminf(ratio_f32(tot_queue, NI), 50.0f);
-            row[NI * 14 + 3] = ratio_f32(tot_passed, NI);
+            row[NI * 14 + 1] = fminf(ratio0_f32(tot_wait, tot_passed > 1 ? tot_passed : 1), 100.0f);
+            row[NI * 14 + 2] = fminf(ratio0_f32(tot_queue, NI), 50.0f);
+            row[NI * 14 + 3] = ratio0_f32(tot_passed, NI);
         }
     } else {
-        // ================= env warp: spawn, reward, termination, global metrics, counters =================
+        // ================= env warp: spawn, reward, termination, counters =================
         int listed = 0;
         double total_reward = 0.0;
         if (active) {
@@ -374,11 +461,13 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
             }
             s_spawn[lane] = spawn;
             cta_barrier();  // barrier 2
+        } else {
+            cta_barrier();  // the reciprocal table is complete
         }
-        // While the intersection warps run phase B: everything of the env's outputs that does not depend on them.
+        // While the intersection warps process the queues: everything of the env's outputs that does not depend on them.
         const int ep_len = timestep;
         if (active) {
-            if (do_reset || same_step) { timestep = 0; flags = 0; }
+            if (wipe) { timestep = 0; flags = 0; }
             else if (ended) flags |= TFLAG_NEEDS_RESET;
             a.st.misc[e32] = (uint32_t)timestep | (flags << 16);
             a.st.misc[2u * un + e32] = ctr;
@@ -390,33 +479,23 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
         }
         cta_barrier();  // barrier 3
 
-        // ---- phase C: _calculate_reward (:287-311); the intersection warps wait for this at barrier 4
+        // ---- _calculate_reward (:287-311); the intersection warps wait for this at barrier 4
         double st_ret = 0.0, st_len = 0.0;
         if (active) {
-            int tot_passed = 0, tot_wait = 0, tot_queue = 0;
+            int tot_passed = 0, tot_wait = 0, tot_queue = 0, left = 0;
             for (int i = 0; i < NI; ++i) {
                 tot_passed += s_part[(0 * NI + i) * WPI_E + lane];
                 tot_wait += s_part[(1 * NI + i) * WPI_E + lane];
                 tot_queue += s_part[(2 * NI + i) * WPI_E + lane];
-                listed -= s_part[(3 * NI + i) * WPI_E + lane];
+                left += s_part[(3 * NI + i) * WPI_E + lane];
             }
             double rew = 0.0;
             if (do_reset) {
                 total_reward = 0.0;
                 listed = 0;
             } else if (!IS_RESET) {
-                // CUMULATIVE counters, float64, the reference's order of additions
-                rew += (double)tot_passed * 1.0;
-                rew += (double)tot_wait * -0.1;
-                rew += (double)tot_queue * -0.05;
-                if (NI > 1) {
-                    const int32_t *q = s_part + 2 * NI * WPI_E + lane;  // queue total of intersection i at q[i * 32]
-                    const double mean = np_sum_fn([&](int i) { return (double)q[i * WPI_E]; }, NI) / (double)NI;
-                    const double var =
-                        np_sum_fn([&](int i) { const double dq = (double)q[i * WPI_E] - mean; return dq * dq; }, NI) /
-                        (double)NI;  // np.var: population variance
-                    rew += 0.5 / (1 + var);
-                }
+                listed -= left;
+                rew = step_reward<NI_T>(tot_passed, tot_wait, tot_queue, s_part + 2 * NI * WPI_E + lane, WPI_E, NI);
                 total_reward += rew;
             }
             if (ended) {
@@ -470,12 +549,12 @@ __global__ void __maxnreg__(MAXREG) traffic_wpi_kernel(const TArgs a) {
 }
 
 template <int NI_T, int IPW, int MAXREG, bool IS_RESET>
-int launch_wpi(const TArgs &a, cudaStream_t stream) {
+int launch_shape(const TArgs &a, cudaStream_t stream) {
     const int od = a.ni * 14 + 4, nw = (a.ni + IPW - 1) / IPW;
-    const size_t smem = (size_t)WPI_E * od * sizeof(float) +
+    const size_t smem = 256 * sizeof(double) + (size_t)WPI_E * od * sizeof(float) +
                         (size_t)(4 * a.ni * WPI_E + WPI_E + SPEC_BLOCKS * 4 * WPI_E + a.ni) * sizeof(int32_t);
     const unsigned grid = (unsigned)((a.n + WPI_E - 1) / WPI_E);
-    auto kern = traffic_wpi_kernel<NI_T, IPW, MAXREG, IS_RESET>;
+    auto kern = traffic_step_kernel<NI_T, IPW, MAXREG, IS_RESET>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_pdl(kern, dim3(grid), dim3((nw + 1) * 32), smem, stream, a);
@@ -485,11 +564,24 @@ int launch_wpi(const TArgs &a, cudaStream_t stream) {
 
 template <bool IS_RESET>
 int launch(const TArgs &a, cudaStream_t stream) {
-    // Default grid (9 intersections): 2 intersections per warp, 6-warp CTAs capped at 64 registers.  Same-box sweep at
-    // 65,536 envs, us per step: (1/warp, 48 regs) 30.6, (2, 56) 29.4, (2, 64) 28.6, (2, 72) 32.6, (3, 64) 29.0,
-    // (3, 72) 28.5, (3, 80) 30.9 -- and (2, 56/64) is the best pair at 1M envs (328 / 338 us).
-    if (a.ni == 9) return launch_wpi<9, 2, 64, IS_RESET>(a, stream);
-    return launch_wpi<0, 1, 72, IS_RESET>(a, stream);
+    // Default grid (9 intersections): 3 intersections per warp, 4-warp CTAs capped at 72 registers (7 CTAs per SM, the
+    // 2048 CTAs of 65,536 envs are 1.98 waves).  Same-box sweep, us per step at 65,536 / 1,048,576 envs (L2 flushed):
+    // (intersections per warp, registers) (1, 40) 30.4 / 256, (2, 48) 29.7 / 263, (2, 56) 28.3-29.0 / 225-253,
+    // (2, 64) 28.1-28.5 / 250-258, (3, 64) 30.7 / 255, **(3, 72) 28.2 / 223-225**, (3, 80) 30.3 / 233.
+    // BENG_TRAFFIC_CFG="ipw,maxreg" selects one of the other instantiated shapes for A/B runs.
+    if (a.ni == 9) {
+        if (const char *cfg = getenv("BENG_TRAFFIC_CFG")) {
+            int ipw = 0, maxreg = 0;
+            if (sscanf(cfg, "%d,%d", &ipw, &maxreg) == 2) {
+                if (ipw == 2 && maxreg == 56) return launch_shape<9, 2, 56, IS_RESET>(a, stream);
+                if (ipw == 2 && maxreg == 64) return launch_shape<9, 2, 64, IS_RESET>(a, stream);
+                if (ipw == 3 && maxreg == 72) return launch_shape<9, 3, 72, IS_RESET>(a, stream);
+            }
+            return BENG_ERR_BAD_ARG;
+        }
+        return launch_shape<9, 3, 72, IS_RESET>(a, stream);
+    }
+    return launch_shape<0, 1, 72, IS_RESET>(a, stream);
 }
 
 int check(const beng_traffic_params *p, const beng_traffic_state *st, const beng_traffic_io *io, int64_t n) {
@@ -517,6 +609,7 @@ TArgs make_args(const beng_traffic_params *p, const beng_traffic_state *st, cons
     a.n = n;
     const int cells = p->grid_rows * p->grid_cols;
     a.ni = p->num_intersections < cells ? p->num_intersections : cells;
+    a.inv_cols = (65536u + (uint32_t)p->grid_cols - 1u) / (uint32_t)p->grid_cols;
     return a;
 }
 

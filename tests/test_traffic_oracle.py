@@ -108,3 +108,40 @@ def test_c_oracle_matches_live_reference():
                 obs, _ = env.reset()
             assert r == orc.reward64[e] and term == bool(orc.terminated[e]) and np.array_equal(obs, orc.obs[e])
             assert rr.counter == st["rng_counter"][e]
+
+
+def test_kernel_arithmetic_shortcuts_are_exact():
+    """The step kernel replaces three IEEE divisions by cheaper sequences (csrc/traffic.cu: div_const, the reciprocal
+    table of the mean waiting time, the multiply-shift for start // cols).  Each is restated here in exact rational
+    arithmetic / NumPy and compared with the division it stands for."""
+    from fractions import Fraction as F
+
+    rng = np.random.default_rng(7)
+    # (a) div_const<9>: q = RN(x*y), r = fma(-9, q, x), result = fma(r, y, q) with y = RN(1/9)  ==  x / 9
+    y = 1.0 / 9.0
+
+    def div9(x):
+        q = x * y
+        r = float(F(x) - 9 * F(q))            # an FMA rounds the exact expression once
+        return float(F(q) + F(r) * F(y))
+
+    xs = [float(s) for s in range(0, 9181)]    # every possible sum of nine queue totals (9 * 4 * 255)
+    for _ in range(20000):                     # sums of squared deviations as _calculate_reward forms them
+        q = rng.integers(0, 60, size=9).astype(np.float64)
+        xs.append(float(np.sum((q - np.sum(q) / 9.0) ** 2)))
+    xs += list(rng.random(5000) * 2.0 ** rng.integers(-40, 40, size=5000))
+    assert all(div9(x) == x / 9.0 for x in xs)
+
+    # (b) float32(qw / cnt) == float32(float64(qw) * RN(1/cnt)) below the 100.0 clamp (and both sides clamp above it)
+    cnt = np.arange(1, 256, dtype=np.int64)
+    rcp = 1.0 / cnt.astype(np.float64)
+    for qw in [np.arange(0, 4096, dtype=np.int64), rng.integers(0, 1 << 24, size=8192), rng.integers(0, 1 << 31, size=8192)]:
+        a = qw[:, None].astype(np.float64)
+        ref = np.minimum((a / cnt[None, :]).astype(np.float32), np.float32(100.0))
+        got = np.minimum((a * rcp[None, :]).astype(np.float32), np.float32(100.0))
+        assert np.array_equal(ref, got)
+
+    # (c) start // cols for start < 25 as (start * ceil(2^16 / cols)) >> 16
+    for cols in list(range(1, 4000)) + [65535, 65536, 65537, (1 << 31) - 1]:
+        inv = (65536 + cols - 1) // cols
+        assert all((s * inv) >> 16 == s // cols for s in range(25))
