@@ -401,8 +401,8 @@ def kernel_description(lib, env_name, n):
         return "beng::climate_kernel<T=128,IS_RESET=false>: one thread per env, 128-env tile per CTA, 8 CTAs per SM"
     if env_name == "builder":
         return "beng::builder_kernel<T=64,IS_RESET=false>: one thread per env, 64-env grid tile per CTA"
-    return ("beng::traffic_wpi_kernel<NI=9,IS_RESET=false>: 192-thread CTA per 32 envs, five intersection warps (2 each) + "
-            "one env warp")
+    return ("beng::traffic_step_kernel<NI=9,IPW=3,72 regs,IS_RESET=false>: 128-thread CTA per 32 envs, three intersection "
+            "warps (3 intersections each) + one env warp, 7 CTAs/SM")
 
 
 API_NAMES = {"snake": "BatchedSnakeEnv.step_host -> beng_snake_step_host",

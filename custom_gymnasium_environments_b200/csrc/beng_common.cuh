@@ -83,4 +83,17 @@ __device__ __forceinline__ long long ld_stream_s64(const long long *p) {
     return r;
 }
 
+// Correctly rounded x / B (float64) for a compile-time integer B without the IEEE division subroutine (a ~60-instruction
+// call on sm_100a): y = RN(1 / B), q = RN(x * y), r = x - B * q exactly (FMA), result RN(q + r * y) -- Markstein's
+// final iteration, which returns the correctly rounded quotient when y is the correctly rounded reciprocal and q is
+// within an ulp of x / B.  For finite x whose quotient neither overflows nor is subnormal (the callers divide sums of
+// small integers).  tests/test_traffic_oracle.py restates the sequence in exact rational arithmetic against x / B.
+template <int B>
+__device__ __forceinline__ double div_const(double x) {
+    constexpr double y = 1.0 / (double)B;
+    const double q = x * y;
+    const double r = fma(-(double)B, q, x);
+    return fma(r, y, q);
+}
+
 }  // namespace beng

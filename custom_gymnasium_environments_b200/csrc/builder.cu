@@ -32,11 +32,12 @@ struct BArgs {
     int first_call;
 };
 
-template <int T, bool IS_RESET>
+// CELLS_T: G*G when it is known at compile time and a multiple of 4 (the default 10 x 10 board), 0 = any board.
+template <int T, bool IS_RESET, int CELLS_T>
 __global__ void __launch_bounds__(T) builder_kernel(const BArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ int s_stats[4];  // per-CTA: n_episodes, sum_return, sum_length, wins
-    const int G = a.p.grid_size, cells = G * G, FD = cells + 6;
+    const int cells = CELLS_T ? CELLS_T : a.p.grid_size * a.p.grid_size, FD = cells + 6;
     uint8_t *tile = smem_raw;                                                     // [T][cells]
     float *flat = reinterpret_cast<float *>(smem_raw + (((size_t)T * cells + 15) & ~(size_t)15));  // [T][cells + 6]
     const int tid = threadIdx.x;
@@ -118,8 +119,31 @@ __global__ void __launch_bounds__(T) builder_kernel(const BArgs a) {
                     bool ok = (action == FARM) ? wood >= 5 : (action == LUMBERYARD) ? stone >= 3
                             : (action == QUARRY) ? wood >= 5 : (wood >= 10 && stone >= 5);  // _can_afford_building
                     int n_empty = 0;
+                    [[maybe_unused]] uint32_t emp[CELLS_T ? (CELLS_T / 4 + 7) / 8 : 1];  // bit c set <=> cell c is empty
                     if (ok) {
-                        if (wordwise) {  // __vcmpeq4: 0xFF in every byte lane that equals zero
+                        if constexpr (CELLS_T != 0) {
+                            // Occupancy bitmap of the row, 4 cells per shared-memory word.  Cell values are 0..4, so
+                            // adding 0x7F to every byte lane sets its top bit exactly when the cell is occupied (no
+                            // carry between lanes); one multiply-high gathers the four top bits into a nibble.
+                            // (The first version counted the empty cells in one pass over the row and searched the
+                            // k-th in a second: 45 % of the kernel's instructions, issue slots 68 % busy.)
+                            constexpr int NWORD = CELLS_T / 4, NMASK = (NWORD + 7) / 8;
+                            uint32_t occ[NMASK];
+#pragma unroll
+                            for (int m = 0; m < NMASK; ++m) occ[m] = 0;
+#pragma unroll
+                            for (int i = 0; i < NWORD; ++i) {
+                                const uint32_t top = (row32[i] + 0x7F7F7F7Fu) & 0x80808080u;  // bits 7, 15, 23, 31
+                                const uint32_t nib = __umulhi(top, (1u << 25) | (1u << 18) | (1u << 11) | (1u << 4)) & 0xFu;
+                                occ[i >> 3] |= nib << ((i & 7) * 4);
+                            }
+#pragma unroll
+                            for (int m = 0; m < NMASK; ++m) {
+                                const int bits = CELLS_T - 32 * m;  // cells covered by this word
+                                emp[m] = ~occ[m] & (bits >= 32 ? 0xFFFFFFFFu : ((1u << (bits & 31)) - 1u));
+                                n_empty += __popc(emp[m]);
+                            }
+                        } else if (wordwise) {  // __vcmpeq4: 0xFF in every byte lane that equals zero
                             for (int i = 0; i < (cells >> 2); ++i) n_empty += __popc(__vcmpeq4(row32[i], 0u)) >> 3;
                         } else {
                             for (int i = 0; i < cells; ++i) n_empty += (row[i] == 0);
@@ -129,7 +153,27 @@ __global__ void __launch_bounds__(T) builder_kernel(const BArgs a) {
                     if (ok) {
                         int idx = rng.randint(0, n_empty - 1);  // np.random.randint(n_empty), :137
                         int pos = 0;
-                        if (wordwise) {
+                        if constexpr (CELLS_T != 0) {
+                            constexpr int NMASK = (CELLS_T / 4 + 7) / 8;
+                            uint32_t e = 0;
+                            int cum = 0;
+                            bool found = false;
+#pragma unroll
+                            for (int m = 0; m < NMASK; ++m) {  // the bitmap word that holds the idx-th empty cell
+                                const int c = __popc(emp[m]);
+                                if (!found && idx < cum + c) { e = emp[m]; pos = 32 * m; idx -= cum; found = true; }
+                                cum += c;
+                            }
+                            int t = __popc(e & 0xFFFFu);  // the idx-th set bit of e (0-based), by halves
+                            if (idx >= t) { idx -= t; pos += 16; e >>= 16; }
+                            t = __popc(e & 0xFFu);
+                            if (idx >= t) { idx -= t; pos += 8; e >>= 8; }
+                            t = __popc(e & 0xFu);
+                            if (idx >= t) { idx -= t; pos += 4; e >>= 4; }
+                            t = __popc(e & 0x3u);
+                            if (idx >= t) { idx -= t; pos += 2; e >>= 2; }
+                            if (idx >= (int)(e & 1u)) pos += 1;
+                        } else if (wordwise) {
                             for (int i = 0; i < (cells >> 2); ++i) {
                                 const uint32_t m = __vcmpeq4(row32[i], 0u);
                                 const int c = __popc(m) >> 3;
@@ -260,7 +304,7 @@ int launch(const BArgs &a, cudaStream_t stream) {
     const int cells = a.p.grid_size * a.p.grid_size;
     size_t smem = ((size_t)BUILDER_T * cells + 15) & ~(size_t)15;
     if (a.io.flat_obs) smem += (size_t)BUILDER_T * (cells + 6) * sizeof(float);
-    auto kern = builder_kernel<BUILDER_T, IS_RESET>;
+    auto kern = cells == 100 ? builder_kernel<BUILDER_T, IS_RESET, 100> : builder_kernel<BUILDER_T, IS_RESET, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     e = launch_pdl(kern, dim3((unsigned)((a.n + BUILDER_T - 1) / BUILDER_T)), dim3(BUILDER_T), smem, stream, a);

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
                     lights_on += v;
                 }
                 step = min(step + 1, 65535);
-                const double tod = (double)(step % 1440) / 60.0;  // :91
+                const double tod = div_const<60>((double)(step % 1440));  // :91, (step % 1440) / 60 correctly rounded
                 outside = outside_temp(tod, rng);
                 {   // update_occupancy, utils.py:15-22: rng.choice(values, p) == inverse-CDF lookup
                     const bool day = (9 <= tod && tod < 18);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
         float *row = tile + tid * KOBS;  // env.py:72-82
         row[0] = (float)room;
         row[1] = (float)people;
-        row[2] = (float)((double)(step % 1440) / 60.0);
+        row[2] = (float)div_const<60>((double)(step % 1440));
         row[3] = (float)outside;
         row[4] = (float)ac;
 #pragma unroll

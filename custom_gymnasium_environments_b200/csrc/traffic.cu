@@ -191,18 +191,6 @@ __device__ __forceinline__ void fill_rcp_table(double *rcp, int tid, int nthread
     for (int i = tid; i < 256; i += nthreads) rcp[i] = g_rcp_table.v[i];
 }
 
-// Correctly rounded x / B for a compile-time B without the division subroutine (two of these sit on the env's serial
-// chain): y = RN(1 / B), q = RN(x * y), r = x - B * q exactly (FMA), result RN(q + r * y) -- Markstein's final
-// iteration, which returns the correctly rounded quotient when y is the correctly rounded reciprocal and q is within
-// an ulp of x / B.  (tests/test_traffic_oracle.py checks the sequence against x / 9 on CPU doubles.)
-template <int B>
-__device__ __forceinline__ double div_const(double x) {
-    constexpr double y = 1.0 / (double)B;
-    const double q = x * y;
-    const double r = fma(-(double)B, q, x);
-    return fma(r, y, q);
-}
-
 struct IxOut {
     int pas, wt, qsum, left;
 };

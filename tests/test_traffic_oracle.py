@@ -117,13 +117,18 @@ def test_kernel_arithmetic_shortcuts_are_exact():
     from fractions import Fraction as F
 
     rng = np.random.default_rng(7)
-    # (a) div_const<9>: q = RN(x*y), r = fma(-9, q, x), result = fma(r, y, q) with y = RN(1/9)  ==  x / 9
-    y = 1.0 / 9.0
+    # (a) div_const<B> (csrc/beng_common.cuh): q = RN(x*y), r = fma(-B, q, x), result = fma(r, y, q), y = RN(1/B)  ==  x / B
+    def div_const(x, b):
+        y = 1.0 / b
+        q = x * y
+        r = float(F(x) - b * F(q))            # an FMA rounds the exact expression once
+        return float(F(q) + F(r) * F(y))
 
     def div9(x):
-        q = x * y
-        r = float(F(x) - 9 * F(q))            # an FMA rounds the exact expression once
-        return float(F(q) + F(r) * F(y))
+        return div_const(x, 9)
+
+    # smartclimate's time of day, (step % 1440) / 60 (csrc/climate.cu), uses the same sequence with B = 60
+    assert all(div_const(float(m), 60) == m / 60.0 for m in range(1440))
 
     xs = [float(s) for s in range(0, 9181)]    # every possible sum of nine queue totals (9 * 4 * 255)
     for _ in range(20000):                     # sums of squared deviations as _calculate_reward forms them
