@@ -398,9 +398,11 @@ def kernel_description(lib, env_name, n):
                 "state chain, 112 regs) run up to 16 units ahead of 16 observation warps (64 regs) that compose the 261-float "
                 "rows from a 2-stage TMA tensor-load ring and drain 32-env tiles with bulk stores")
     if env_name == "climate":
-        return "beng::climate_kernel<T=128,IS_RESET=false>: one thread per env, 128-env tile per CTA, 8 CTAs per SM"
+        return ("beng::climate_step_persistent_kernel<T=128>: one thread per env, 5 persistent CTAs per SM walking 128-env "
+                "tiles, the next tile's state and action words requested before the current tile is computed")
     if env_name == "builder":
-        return "beng::builder_kernel<T=64,IS_RESET=false>: one thread per env, 64-env grid tile per CTA"
+        return ("beng::builder_kernel<T=64,IS_RESET=false,CELLS=100>: one thread per env, 64-env grid tile per CTA, "
+                "occupancy bitmap per row")
     return ("beng::traffic_step_kernel<NI=9,IPW=3,72 regs,IS_RESET=false>: 128-thread CTA per 32 envs, three intersection "
             "warps (3 intersections each) + one env warp, 7 CTAs/SM")
 

@@ -40,6 +40,156 @@ __device__ __forceinline__ double outside_temp(double tod, EnvStream &rng) {
     return rng.normal(base, 5.0);
 }
 
+// One env's state and action words as loaded (requested together, before anything is inspected).
+struct KIn {
+    double room, outside, ac, total, energy;
+    uint32_t w0, ctr;
+    int step, comfort_time;
+    float act_ac;
+    uint32_t lw;  // four int8 light flags
+};
+
+template <bool IS_RESET>
+__device__ __forceinline__ KIn load_env(const KArgs &a, long long env) {
+    const long long n = a.n;
+    KIn in;
+    in.act_ac = 0.0f;
+    in.lw = 0;
+    if constexpr (!IS_RESET) {
+        in.act_ac = a.ac_temp[env];
+        in.lw = *reinterpret_cast<const uint32_t *>(a.lights + 4 * env);
+    }
+    in.room = a.st.f64[env]; in.outside = a.st.f64[n + env]; in.ac = a.st.f64[2 * n + env];
+    in.total = a.st.f64[3 * n + env]; in.energy = a.st.f64[4 * n + env];
+    in.w0 = (uint32_t)a.st.i32[env];
+    in.step = a.st.i32[n + env]; in.comfort_time = a.st.i32[2 * n + env];
+    in.ctr = (uint32_t)a.st.i32[3 * n + env];
+    return in;
+}
+
+// reset / step of one env (env.py:62-70, :84-117), its state and result stores, and its observation row
+template <bool IS_RESET>
+__device__ __forceinline__ void step_env(const KArgs &a, long long env, const KIn &in, float *row, bool &ended,
+                                         double &st_ret, double &st_len) {
+    const long long n = a.n;
+    const float act_ac = in.act_ac;
+    const uint32_t lw = in.lw;
+    double room = in.room, outside = in.outside, ac = in.ac, total = in.total, energy = in.energy;
+    const uint32_t w0 = in.w0;
+    int people = w0 & 0xFF, lights = (w0 >> 8) & 0xF;
+    uint32_t flags = w0 >> 16;
+    int step = in.step, comfort_time = in.comfort_time;
+    uint32_t ctr = in.ctr;
+    bool selected = true;
+    if constexpr (IS_RESET) {
+        if (a.mask) selected = a.mask[env] != 0;
+        if (selected && a.first_call) ctr = 0;
+    }
+    EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
+    double rew = 0.0, cf = 0.0, acp = 0.0, lp = 0.0;
+    int term = 0, at_limit = 0;
+
+    auto init_state = [&]() {  // env.py:48-60
+        room = rng.uniform(22.0, 26.0);
+        people = rng.randint(0, a.p.max_occupancy);  // integers(0, max_occupancy + 1)
+        outside = outside_temp(0.0, rng);
+        ac = 24.0;
+        lights = 0;
+        total = 0.0;
+        comfort_time = 0;
+        energy = 0.0;
+        step = 0;
+        flags = 0;
+    };
+
+    if constexpr (IS_RESET) {
+        if (selected) init_state();
+    } else {
+        if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & KFLAG_NEEDS_RESET)) {
+            init_state();
+        } else {
+            ac = kclip((double)act_ac, 16.0, 32.0);  // env.py:85
+            int lights_on = 0;
+            lights = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int v = (int)(int8_t)((lw >> (8 * i)) & 0xFF);
+                lights |= (v & 1) << i;  // MultiBinary(4): 0 / 1
+                lights_on += v;
+            }
+            step = min(step + 1, 65535);
+            const double tod = div_const<60>((double)(step % 1440));  // :91, (step % 1440) / 60 correctly rounded
+            outside = outside_temp(tod, rng);
+            {   // update_occupancy, utils.py:15-22: rng.choice(values, p) == inverse-CDF lookup
+                const bool day = (9 <= tod && tod < 18);
+                const double u = rng.random53();
+                const double c0 = day ? 0x1.999999999999ap-4 : 0x1.9999999999998p-3;
+                const double c1 = day ? 0x1.999999999999ap-2 : 0x1.3333333333333p-1;
+                const double c2 = day ? 0x1.999999999999ap-1 : 0x1.cccccccccccccp-1;
+                const int idx = (c0 <= u) + (c1 <= u) + (c2 <= u);  // searchsorted(cdf, u, side='right')
+                const int change = idx + (day ? -1 : -2);            // [-1,0,1,2] / [-2,-1,0,1]
+                people = min(max(people + change, 0), a.p.max_occupancy);
+            }
+            // room_temp_dynamics, utils.py:24-28
+            const double temp = room + 0.1 * (outside - room) + 0.2 * (ac - room) + (double)people * 1.0;
+            room = kclip(temp, 10.0, 50.0);
+            // calculate_reward, utils.py:30-50
+            if (20 <= room && room <= 24) cf = 10;
+            else if (18 <= room && room <= 26) cf = 5;
+            else if (16 <= room && room <= 28) cf = 0;
+            else cf = -15 * fabs(room - 22);
+            acp = -0.5 * fabs(ac - outside);
+            const int required = min(4, (people + 1) / 2);  // ceil(num_people / 2)
+            lp = -1.0 * (double)max(0, lights_on - required);
+            rew = cf + acp + lp;
+            total += rew;
+            if (20 <= room && room <= 24) comfort_time += 1;
+            energy += fabs(ac - outside) + (double)lights_on;
+            at_limit = step >= a.p.episode_minutes;
+            term = at_limit;  // :107, reported as terminated
+            if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
+                ended = true;
+                st_ret = total;
+                st_len = (double)step;
+                if (a.io.ep_return) a.io.ep_return[env] = total;
+                if (a.io.ep_length) a.io.ep_length[env] = step;
+                if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) init_state();
+                else flags |= KFLAG_NEEDS_RESET;
+            }
+        }
+    }
+
+    // observation row, env.py:72-82
+    row[0] = (float)room;
+    row[1] = (float)people;
+    row[2] = (float)div_const<60>((double)(step % 1440));
+    row[3] = (float)outside;
+    row[4] = (float)ac;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) row[5 + i] = (float)((lights >> i) & 1);
+
+    a.st.f64[env] = room;
+    a.st.f64[n + env] = outside;
+    a.st.f64[2 * n + env] = ac;
+    a.st.f64[3 * n + env] = total;
+    a.st.f64[4 * n + env] = energy;
+    a.st.i32[env] = (int32_t)((uint32_t)people | ((uint32_t)lights << 8) | (flags << 16));
+    a.st.i32[n + env] = step;
+    a.st.i32[2 * n + env] = comfort_time;
+    a.st.i32[3 * n + env] = (int32_t)rng.ctr;
+    if constexpr (!IS_RESET) {
+        a.io.reward[env] = (float)rew;
+        a.io.terminated[env] = (uint8_t)term;
+        if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && at_limit);
+        if (a.io.reward64) a.io.reward64[env] = rew;
+        if (a.io.reward_terms) {
+            a.io.reward_terms[env] = cf;
+            a.io.reward_terms[n + env] = acp;
+            a.io.reward_terms[2 * n + env] = lp;
+        }
+    }
+}
+
 template <int T, bool IS_RESET>
 __global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
     __shared__ __align__(128) float tile[T * KOBS];
@@ -53,128 +203,8 @@ __global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
     bool ended = false;
     double st_ret = 0.0, st_len = 0.0;
     if (env < n) {
-        // the action is requested together with the state, not after the state has arrived and been inspected
-        float act_ac = 0.0f;
-        uint32_t lw = 0;
-        if constexpr (!IS_RESET) {
-            act_ac = a.ac_temp[env];
-            lw = *reinterpret_cast<const uint32_t *>(a.lights + 4 * env);  // four int8 flags
-        }
-        double room = a.st.f64[env], outside = a.st.f64[n + env], ac = a.st.f64[2 * n + env];
-        double total = a.st.f64[3 * n + env], energy = a.st.f64[4 * n + env];
-        const uint32_t w0 = (uint32_t)a.st.i32[env];
-        int people = w0 & 0xFF, lights = (w0 >> 8) & 0xF;
-        uint32_t flags = w0 >> 16;
-        int step = a.st.i32[n + env], comfort_time = a.st.i32[2 * n + env];
-        uint32_t ctr = (uint32_t)a.st.i32[3 * n + env];
-        bool selected = true;
-        if constexpr (IS_RESET) {
-            if (a.mask) selected = a.mask[env] != 0;
-            if (selected && a.first_call) ctr = 0;
-        }
-        EnvStream rng(a.p.seed, a.p.env_id_base + (uint64_t)env, BENG_STREAM_ENV, ctr);
-        double rew = 0.0, cf = 0.0, acp = 0.0, lp = 0.0;
-        int term = 0, at_limit = 0;
-
-        auto init_state = [&]() {  // env.py:48-60
-            room = rng.uniform(22.0, 26.0);
-            people = rng.randint(0, a.p.max_occupancy);  // integers(0, max_occupancy + 1)
-            outside = outside_temp(0.0, rng);
-            ac = 24.0;
-            lights = 0;
-            total = 0.0;
-            comfort_time = 0;
-            energy = 0.0;
-            step = 0;
-            flags = 0;
-        };
-
-        if constexpr (IS_RESET) {
-            if (selected) init_state();
-        } else {
-            if (a.p.autoreset_mode == BENG_AUTORESET_NEXT_STEP && (flags & KFLAG_NEEDS_RESET)) {
-                init_state();
-            } else {
-                ac = kclip((double)act_ac, 16.0, 32.0);  // env.py:85
-                int lights_on = 0;
-                lights = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int v = (int)(int8_t)((lw >> (8 * i)) & 0xFF);
-                    lights |= (v & 1) << i;  // MultiBinary(4): 0 / 1
-                    lights_on += v;
-                }
-                step = min(step + 1, 65535);
-                const double tod = div_const<60>((double)(step % 1440));  // :91, (step % 1440) / 60 correctly rounded
-                outside = outside_temp(tod, rng);
-                {   // update_occupancy, utils.py:15-22: rng.choice(values, p) == inverse-CDF lookup
-                    const bool day = (9 <= tod && tod < 18);
-                    const double u = rng.random53();
-                    const double c0 = day ? 0x1.999999999999ap-4 : 0x1.9999999999998p-3;
-                    const double c1 = day ? 0x1.999999999999ap-2 : 0x1.3333333333333p-1;
-                    const double c2 = day ? 0x1.999999999999ap-1 : 0x1.cccccccccccccp-1;
-                    const int idx = (c0 <= u) + (c1 <= u) + (c2 <= u);  // searchsorted(cdf, u, side='right')
-                    const int change = idx + (day ? -1 : -2);            // [-1,0,1,2] / [-2,-1,0,1]
-                    people = min(max(people + change, 0), a.p.max_occupancy);
-                }
-                // room_temp_dynamics, utils.py:24-28
-                const double temp = room + 0.1 * (outside - room) + 0.2 * (ac - room) + (double)people * 1.0;
-                room = kclip(temp, 10.0, 50.0);
-                // calculate_reward, utils.py:30-50
-                if (20 <= room && room <= 24) cf = 10;
-                else if (18 <= room && room <= 26) cf = 5;
-                else if (16 <= room && room <= 28) cf = 0;
-                else cf = -15 * fabs(room - 22);
-                acp = -0.5 * fabs(ac - outside);
-                const int required = min(4, (people + 1) / 2);  // ceil(num_people / 2)
-                lp = -1.0 * (double)max(0, lights_on - required);
-                rew = cf + acp + lp;
-                total += rew;
-                if (20 <= room && room <= 24) comfort_time += 1;
-                energy += fabs(ac - outside) + (double)lights_on;
-                at_limit = step >= a.p.episode_minutes;
-                term = at_limit;  // :107, reported as terminated
-                if (term && a.p.autoreset_mode != BENG_AUTORESET_DISABLED) {
-                    ended = true;
-                    st_ret = total;
-                    st_len = (double)step;
-                    if (a.io.ep_return) a.io.ep_return[env] = total;
-                    if (a.io.ep_length) a.io.ep_length[env] = step;
-                    if (a.p.autoreset_mode == BENG_AUTORESET_SAME_STEP) init_state();
-                    else flags |= KFLAG_NEEDS_RESET;
-                }
-            }
-        }
-
-        float *row = tile + tid * KOBS;  // env.py:72-82
-        row[0] = (float)room;
-        row[1] = (float)people;
-        row[2] = (float)div_const<60>((double)(step % 1440));
-        row[3] = (float)outside;
-        row[4] = (float)ac;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) row[5 + i] = (float)((lights >> i) & 1);
-
-        a.st.f64[env] = room;
-        a.st.f64[n + env] = outside;
-        a.st.f64[2 * n + env] = ac;
-        a.st.f64[3 * n + env] = total;
-        a.st.f64[4 * n + env] = energy;
-        a.st.i32[env] = (int32_t)((uint32_t)people | ((uint32_t)lights << 8) | (flags << 16));
-        a.st.i32[n + env] = step;
-        a.st.i32[2 * n + env] = comfort_time;
-        a.st.i32[3 * n + env] = (int32_t)rng.ctr;
-        if constexpr (!IS_RESET) {
-            a.io.reward[env] = (float)rew;
-            a.io.terminated[env] = (uint8_t)term;
-            if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && at_limit);
-            if (a.io.reward64) a.io.reward64[env] = rew;
-            if (a.io.reward_terms) {
-                a.io.reward_terms[env] = cf;
-                a.io.reward_terms[n + env] = acp;
-                a.io.reward_terms[2 * n + env] = lp;
-            }
-        }
+        const KIn in = load_env<IS_RESET>(a, env);
+        step_env<IS_RESET>(a, env, in, tile + tid * KOBS, ended, st_ret, st_len);
     }
 
     fence_proxy_async_smem();
@@ -208,10 +238,93 @@ __global__ void __launch_bounds__(T, 8) climate_kernel(const KArgs a) {
     if (tid == 0) bulk_wait_read<0>();
 }
 
+// Step kernel, persistent form: a CTA walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ... and requests the NEXT
+// tile's state and action words before it computes the current one, so that the memory round trip of a tile (40 % of
+// the one-tile kernel's stall samples) runs under the float64 arithmetic of the previous one.  Three observation
+// buffers: the bulk copy of tile k is only awaited before tile k+2 is drained, one CTA barrier per tile.
+template <int T, int MINB>
+__global__ void __launch_bounds__(T, MINB) climate_step_persistent_kernel(const KArgs a) {
+    __shared__ __align__(128) float tiles[3][T * KOBS];
+    const int tid = threadIdx.x;
+    const long long n = a.n;
+    const long long n_tiles = (n + T - 1) / T;
+    pdl_launch_dependents();
+    pdl_wait();
+
+    long long tile = blockIdx.x;
+    KIn cur{};
+    if (tile < n_tiles && tile * T + tid < n) cur = load_env<false>(a, tile * T + tid);
+    int b = 0;
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const long long first = tile * T, env = first + tid;
+        const long long env_next = (tile + gridDim.x) * T + tid;
+        KIn nxt{};
+        if (env_next < n) nxt = load_env<false>(a, env_next);  // (past the last tile env_next >= n)
+        float *buf = tiles[b];
+        bool ended = false;
+        double st_ret = 0.0, st_len = 0.0;
+        if (env < n) step_env<false>(a, env, cur, buf + tid * KOBS, ended, st_ret, st_len);
+        fence_proxy_async_smem();
+        if (tid == 0) bulk_wait_read<1>();  // the buffer the NEXT tile writes (drained two tiles ago) is free
+        __syncthreads();
+        if (tid == 0) {
+            const long long n_here = min((long long)T, n - first);
+            const uint32_t bytes = (uint32_t)(n_here * KOBS * sizeof(float));
+            const uint32_t bulk = bytes & ~15u;
+            if (bulk) bulk_store_s2g(a.io.obs + first * KOBS, buf, bulk);
+            bulk_commit();
+            for (uint32_t i = bulk / 4; i < bytes / 4; ++i) a.io.obs[first * KOBS + i] = buf[i];  // ragged last tile
+        }
+        if (a.io.stats) {
+            const unsigned done_mask = __ballot_sync(0xFFFFFFFFu, ended);
+            if (done_mask) {
+                double r = st_ret, l = st_len;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    r += __shfl_xor_sync(0xFFFFFFFFu, r, o);
+                    l += __shfl_xor_sync(0xFFFFFFFFu, l, o);
+                }
+                if ((tid & 31) == 0) {
+                    atomicAdd(&a.io.stats[0], (double)__popc(done_mask));
+                    atomicAdd(&a.io.stats[1], r);
+                    atomicAdd(&a.io.stats[2], l);
+                }
+            }
+        }
+        cur = nxt;
+        b = b == 2 ? 0 : b + 1;
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
 constexpr int CLIMATE_T = 128;
+
+template <int T, int MINB>
+int launch_persistent(const KArgs &a, cudaStream_t stream) {
+    const long long n_tiles = (a.n + T - 1) / T;
+    const long long slots = (long long)device_sm_count() * MINB;
+    const unsigned grid = (unsigned)(n_tiles < slots ? n_tiles : slots);
+    cudaError_t e = launch_pdl(climate_step_persistent_kernel<T, MINB>, dim3(grid), dim3(T), 0, stream, a);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return (int)e;
+}
 
 template <bool IS_RESET>
 int launch(const KArgs &a, cudaStream_t stream) {
+    if constexpr (!IS_RESET) {
+        // Default: 5 persistent CTAs of 128 threads per SM (94 registers, no spills).  Same-box A/B at 1,048,576 envs, L2
+        // flushed, us per step: the one-tile kernel 47.1; persistent (CTAs per SM x threads) 5 x 128 **41.1**, 10 x 64
+        // 41.2, 4 x 128 42.8, 3 x 192 43.3, 2 x 256 44.6; shapes that need a register cap below 94 spill and are slower
+        // than the one-tile kernel (6 x 128 at 80 registers 53.8, 8 x 128 at 64 registers 58.4).
+        // BENG_CLIMATE_CFG = "tile" | "p4" | "p10" selects the others (A/B runs, profiles/cfg_probe.py).
+        if (const char *cfg = getenv("BENG_CLIMATE_CFG")) {
+            if (cfg[0] == 'p' && atoi(cfg + 1) == 4) return launch_persistent<128, 4>(a, stream);
+            if (cfg[0] == 'p' && atoi(cfg + 1) == 10) return launch_persistent<64, 10>(a, stream);
+            if (cfg[0] != 't') return BENG_ERR_BAD_ARG;
+        } else {
+            return launch_persistent<128, 5>(a, stream);
+        }
+    }
     const unsigned grid = (unsigned)((a.n + CLIMATE_T - 1) / CLIMATE_T);
     cudaError_t e = launch_pdl(climate_kernel<CLIMATE_T, IS_RESET>, dim3(grid), dim3(CLIMATE_T), 0, stream, a);
     g_launch_count.fetch_add(1, std::memory_order_relaxed);
