@@ -137,23 +137,22 @@ __device__ __forceinline__ void spawn_route(const TArgs &a, Stream &rng, int &st
 // `if (wipe)` regions executed with 2-4 live lanes, and another fifth in IEEE float divisions (the mean waiting time
 // of every queue) that mostly took the slow path because the numerator was 0.
 struct IxState {
-    uint32_t l0, qm[4];  // light word, queue meta words as loaded
+    uint32_t l0, cnt4, lb4;  // light word; queue lengths / loop-back counts of the four directions, one byte each
     int passed, wait, qw[4];
 };
 
 __device__ __forceinline__ void load_ix(const TArgs &a, uint32_t i, uint32_t un, uint32_t e32, bool ok, IxState &s) {
-    s.l0 = 0; s.passed = 0; s.wait = 0;
+    s.l0 = 0; s.cnt4 = 0; s.lb4 = 0; s.passed = 0; s.wait = 0;
 #pragma unroll
-    for (int d = 0; d < 4; ++d) { s.qm[d] = 0; s.qw[d] = 0; }
+    for (int d = 0; d < 4; ++d) s.qw[d] = 0;
     if (ok) {
         s.l0 = a.st.light[i * un + e32];
         s.passed = a.st.passed[i * un + e32];
         s.wait = a.st.waiting[i * un + e32];
+        s.cnt4 = a.st.qmeta[(i * 2) * un + e32];
+        s.lb4 = a.st.qmeta[(i * 2 + 1) * un + e32];
 #pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            s.qm[d] = a.st.qmeta[(i * 4 + d) * un + e32];
-            s.qw[d] = a.st.qwait[(i * 4 + d) * un + e32];
-        }
+        for (int d = 0; d < 4; ++d) s.qw[d] = a.st.qwait[(i * 4 + d) * un + e32];
     }
 }
 
@@ -203,34 +202,34 @@ struct IxOut {
 __device__ __forceinline__ IxOut process_ix(const TArgs &a, int NI, int i, uint32_t un, uint32_t e32, const IxState &s,
                                             int ph, int tm, bool stepping, bool wipe, int spq, int sp_lb, float *row,
                                             const double *rcp) {
+    // The four queues of an intersection are stepped together on their packed byte lanes (N, E, S, W = lanes 0..3;
+    // a lane never exceeds 255 because len(self.vehicles) <= 255): `go` lanes empty into vehicles_passed, `wait`
+    // lanes add their length to the waiting times; byte sums are one dot-product instruction (dp4a) each.
     const bool go_ns = stepping && ph == NS_GREEN, go_ew = stepping && ph == EW_GREEN;      // can_pass
-    const bool wait_ns = stepping && ph != NS_GREEN, wait_ew = stepping && ph != EW_GREEN;
-    int pas = s.passed, wt = s.wait, qsum = 0, left = 0;
-    uint32_t qm_new[4];
+    const uint32_t gm = go_ns ? 0x00FF00FFu : go_ew ? 0xFF00FF00u : 0u;
+    const uint32_t wm = stepping ? ~gm : 0u;
+    const uint32_t hit = (spq >> 2) == i ? 1u << ((spq & 3) * 8) : 0u;  // add_vehicle_to_queue, waiting_time 0
+    uint32_t cnt4 = s.cnt4 + hit, lb4 = s.lb4 + (sp_lb ? hit : 0u);
+    const uint32_t wait4 = cnt4 & wm;                                   // every queued vehicle waits one more step
+    const int pas = s.passed + (int)__dp4a(cnt4 & gm, 0x01010101u, 0u);  // the whole queue proceeds ...
+    const int left = (int)__dp4a(lb4 & gm, 0x01010101u, 0u);             // ... loop-back vehicles leave self.vehicles
+    const int wt = s.wait + (int)__dp4a(wait4, 0x01010101u, 0u);
+    cnt4 &= ~gm;
+    lb4 &= ~gm;
+    const int qsum = (int)__dp4a(cnt4, 0x01010101u, 0u);
     int qw_new[4];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) {  // N, E, S, W
-        const bool go = (d & 1) ? go_ew : go_ns, wait = (d & 1) ? wait_ew : wait_ns;
-        const uint32_t qi = (uint32_t)(i * 4 + d) * un + e32;
-        int cnt = (int)(s.qm[d] & 0xFF), lb = (int)(s.qm[d] >> 8);
-        const int hit = spq == i * 4 + d;  // add_vehicle_to_queue, waiting_time 0
-        cnt += hit;
-        lb += hit & sp_lb;
-        pas += go ? cnt : 0;               // the whole queue proceeds; loop-back vehicles leave self.vehicles
-        left += go ? lb : 0;
-        wt += wait ? cnt : 0;              // every queued vehicle waits one more step
-        int qw = s.qw[d] + (wait ? cnt : 0);
-        cnt = go ? 0 : cnt;
-        lb = go ? 0 : lb;
-        qw = go ? 0 : qw;
-        qsum += cnt;
-        qm_new[d] = (uint32_t)cnt | ((uint32_t)lb << 8);
+    for (int d = 0; d < 4; ++d) {
+        const bool go = (d & 1) ? go_ew : go_ns;
+        const int cnt = (int)((cnt4 >> (8 * d)) & 0xFFu);
+        const int qw = go ? 0 : s.qw[d] + (int)((wait4 >> (8 * d)) & 0xFFu);
         qw_new[d] = qw;
-        if (qm_new[d] != s.qm[d]) a.st.qmeta[qi] = (uint16_t)qm_new[d];
-        if (qw != s.qw[d]) a.st.qwait[qi] = qw;
+        if (qw != s.qw[d]) a.st.qwait[(uint32_t)(i * 4 + d) * un + e32] = qw;
         row[NI * 4 + i * 4 + d] = (float)min(cnt, 20);                            // MAX_QUEUE_LENGTH
         row[NI * 8 + i * 4 + d] = fminf((float)((double)qw * rcp[cnt]), 100.0f);   // mean waiting time, <= 100
     }
+    if (cnt4 != s.cnt4) a.st.qmeta[(uint32_t)(i * 2) * un + e32] = cnt4;
+    if (lb4 != s.lb4) a.st.qmeta[(uint32_t)(i * 2 + 1) * un + e32] = lb4;
     const uint32_t nl = (uint32_t)ph | ((uint32_t)tm << 8);
     if (nl != s.l0) a.st.light[(uint32_t)i * un + e32] = (uint16_t)nl;
     if (pas != s.passed) a.st.passed[(uint32_t)i * un + e32] = pas;
@@ -240,11 +239,11 @@ __device__ __forceinline__ IxOut process_ix(const TArgs &a, int NI, int i, uint3
     row[NI * 12 + i * 2] = (float)pas;
     row[NI * 12 + i * 2 + 1] = (float)min(wt, 1000);
     if (wipe) {  // rare (episode boundaries): zero whatever the step left non-zero, observation of a fresh env
+        if (cnt4) a.st.qmeta[(uint32_t)(i * 2) * un + e32] = 0;
+        if (lb4) a.st.qmeta[(uint32_t)(i * 2 + 1) * un + e32] = 0;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-            const uint32_t qi = (uint32_t)(i * 4 + d) * un + e32;
-            if (qm_new[d]) a.st.qmeta[qi] = 0;
-            if (qw_new[d]) a.st.qwait[qi] = 0;
+            if (qw_new[d]) a.st.qwait[(uint32_t)(i * 4 + d) * un + e32] = 0;
             row[NI * 4 + i * 4 + d] = 0.0f;
             row[NI * 8 + i * 4 + d] = 0.0f;
         }
@@ -553,9 +552,11 @@ int launch_shape(const TArgs &a, cudaStream_t stream) {
 template <bool IS_RESET>
 int launch(const TArgs &a, cudaStream_t stream) {
     // Default grid (9 intersections): 3 intersections per warp, 4-warp CTAs capped at 72 registers (7 CTAs per SM, the
-    // 2048 CTAs of 65,536 envs are 1.98 waves).  Same-box sweep, us per step at 65,536 / 1,048,576 envs (L2 flushed):
-    // (intersections per warp, registers) (1, 40) 30.4 / 256, (2, 48) 29.7 / 263, (2, 56) 28.3-29.0 / 225-253,
-    // (2, 64) 28.1-28.5 / 250-258, (3, 64) 30.7 / 255, **(3, 72) 28.2 / 223-225**, (3, 80) 30.3 / 233.
+    // 2048 CTAs of 65,536 envs are 1.98 waves).  Same-box sweeps, us per step at 65,536 / 1,048,576 envs (L2 flushed),
+    // (intersections per warp, registers): before the queues were packed (1, 40) 30.4 / 256, (2, 48) 29.7 / 263,
+    // (2, 56) 28.3-29.0 / 225-253, (2, 64) 28.1-28.5 / 250-258, (3, 64) 30.7 / 255, (3, 72) 28.2 / 223, (3, 80) 30.3 / 233;
+    // with packed queues (2, 56) 28.2 / 220, (2, 64) 28.3 / 229, (3, 56) 28.9 / 230, (3, 64) 27.7 / 234,
+    // **(3, 72) 26.3-27.8 / 217**, (5, 80) 30.8 / 292, (5, 96) 31.7 / 285, (9, 128) 36.0 / 372.
     // BENG_TRAFFIC_CFG="ipw,maxreg" selects one of the other instantiated shapes for A/B runs.
     if (a.ni == 9) {
         if (const char *cfg = getenv("BENG_TRAFFIC_CFG")) {

@@ -70,7 +70,7 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
             self._light = z(ni, n, dt=torch.int16)
             self._passed = z(ni, n, dt=torch.int32)
             self._waiting = z(ni, n, dt=torch.int32)
-            self._qmeta = z(ni * 4, n, dt=torch.int16)
+            self._qmeta = z(ni * 2, n, dt=torch.int32)  # rows 2i / 2i+1: queue lengths / loop-back counts, a byte per direction
             self._qwait = z(ni * 4, n, dt=torch.int32)
             self._misc = z(3, n, dt=torch.int32)
             self._total_reward = z(n, dt=torch.float64)
@@ -131,7 +131,8 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
     @property
     def queue_lengths(self):
         """(n, ni, 4) queue lengths, directions N, E, S, W."""
-        return (self._qmeta.to(torch.int32) & 0xFF).t().reshape(self.num_envs, self.num_intersections, 4)
+        packed = self._qmeta[0::2].t().unsqueeze(-1)  # (n, ni, 1) int32, one byte lane per direction
+        return (packed >> torch.tensor([0, 8, 16, 24], device=packed.device, dtype=torch.int32)) & 0xFF
 
     @property
     def queue_waiting_sums(self):
@@ -141,7 +142,7 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
         """calculate_traffic_metrics (utils.py:251-267) for every env, computed on the device on demand."""
         passed = self._passed.sum(0).double()
         waiting = self._waiting.sum(0).double()
-        queued = (self._qmeta.to(torch.int32) & 0xFF).sum(0).double()
+        queued = self.queue_lengths.sum((1, 2)).double()
         ni = float(self.num_intersections)
         return {"total_vehicles_passed": passed, "total_waiting_time": waiting,
                 "average_waiting_time": waiting / passed.clamp(min=1), "total_queue_length": queued,

@@ -262,7 +262,8 @@ typedef struct beng_traffic_state {
     uint16_t *light;      /* [ni][n]    phase (low byte: 0 NS_GREEN 1 NS_YELLOW 2 EW_GREEN 3 EW_YELLOW) | timer << 8 */
     int32_t *passed;      /* [ni][n]    Intersection.vehicles_passed */
     int32_t *waiting;     /* [ni][n]    Intersection.total_waiting_time */
-    uint16_t *qmeta;      /* [ni*4][n]  queue length | loop-back vehicles << 8, directions N, E, S, W */
+    uint32_t *qmeta;      /* [ni*2][n]  row 2i: queue lengths of intersection i, one byte per direction N, E, S, W (byte 0 = N);
+                                        row 2i+1: loop-back vehicles (route ends where it started) per direction, same lanes */
     int32_t *qwait;       /* [ni*4][n]  sum of Vehicle.waiting_time over the queue */
     uint32_t *misc;       /* [3][n]     current_timestep | flags << 16 ; len(self.vehicles) ; rng_counter */
     double *total_reward; /* [n]        running episode return (info["total_reward"]) */
