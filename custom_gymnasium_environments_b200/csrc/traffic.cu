@@ -217,7 +217,9 @@ __device__ __forceinline__ IxOut process_ix(const TArgs &a, int NI, int i, uint3
     cnt4 &= ~gm;
     lb4 &= ~gm;
     const int qsum = (int)__dp4a(cnt4, 0x01010101u, 0u);
+    // (observation rows are 8-byte aligned and every feature group starts on an even float: pairs go out as float2)
     int qw_new[4];
+    float qlen[4], qmean[4];
 #pragma unroll
     for (int d = 0; d < 4; ++d) {
         const bool go = (d & 1) ? go_ew : go_ns;
@@ -225,19 +227,23 @@ __device__ __forceinline__ IxOut process_ix(const TArgs &a, int NI, int i, uint3
         const int qw = go ? 0 : s.qw[d] + (int)((wait4 >> (8 * d)) & 0xFFu);
         qw_new[d] = qw;
         if (qw != s.qw[d]) a.st.qwait[(uint32_t)(i * 4 + d) * un + e32] = qw;
-        row[NI * 4 + i * 4 + d] = (float)min(cnt, 20);                            // MAX_QUEUE_LENGTH
-        row[NI * 8 + i * 4 + d] = fminf((float)((double)qw * rcp[cnt]), 100.0f);   // mean waiting time, <= 100
+        qlen[d] = (float)min(cnt, 20);                                    // MAX_QUEUE_LENGTH
+        qmean[d] = fminf((float)((double)qw * rcp[cnt]), 100.0f);         // mean waiting time, <= 100
     }
+    float2 *row2 = reinterpret_cast<float2 *>(row);
+    row2[(NI * 4 + i * 4) / 2] = make_float2(qlen[0], qlen[1]);
+    row2[(NI * 4 + i * 4) / 2 + 1] = make_float2(qlen[2], qlen[3]);
+    row2[(NI * 8 + i * 4) / 2] = make_float2(qmean[0], qmean[1]);
+    row2[(NI * 8 + i * 4) / 2 + 1] = make_float2(qmean[2], qmean[3]);
     if (cnt4 != s.cnt4) a.st.qmeta[(uint32_t)(i * 2) * un + e32] = cnt4;
     if (lb4 != s.lb4) a.st.qmeta[(uint32_t)(i * 2 + 1) * un + e32] = lb4;
     const uint32_t nl = (uint32_t)ph | ((uint32_t)tm << 8);
     if (nl != s.l0) a.st.light[(uint32_t)i * un + e32] = (uint16_t)nl;
     if (pas != s.passed) a.st.passed[(uint32_t)i * un + e32] = pas;
     if (wt != s.wait) a.st.waiting[(uint32_t)i * un + e32] = wt;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) row[i * 4 + q] = (ph == q) ? 1.0f : 0.0f;
-    row[NI * 12 + i * 2] = (float)pas;
-    row[NI * 12 + i * 2 + 1] = (float)min(wt, 1000);
+    row2[i * 2] = make_float2(ph == 0 ? 1.0f : 0.0f, ph == 1 ? 1.0f : 0.0f);
+    row2[i * 2 + 1] = make_float2(ph == 2 ? 1.0f : 0.0f, ph == 3 ? 1.0f : 0.0f);
+    row2[NI * 6 + i] = make_float2((float)pas, (float)min(wt, 1000));
     if (wipe) {  // rare (episode boundaries): zero whatever the step left non-zero, observation of a fresh env
         if (cnt4) a.st.qmeta[(uint32_t)(i * 2) * un + e32] = 0;
         if (lb4) a.st.qmeta[(uint32_t)(i * 2 + 1) * un + e32] = 0;
@@ -320,7 +326,6 @@ __global__ void __maxnreg__(MAXREG) traffic_step_kernel(const TArgs a) {
     const uint32_t un = (uint32_t)n, e32 = (uint32_t)env;
     float *row = tile + lane * OD;
     auto cta_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"r"((NW + 1) * 32) : "memory"); };
-    fill_rcp_table(s_rcp, threadIdx.x, (NW + 1) * 32);
     pdl_launch_dependents();
     pdl_wait();
 
@@ -357,6 +362,9 @@ __global__ void __maxnreg__(MAXREG) traffic_step_kernel(const TArgs a) {
             if constexpr (!IS_RESET)
                 if (active && i < NI) act[k] = a.actions[e32 * (uint32_t)NI + (uint32_t)i];
         }
+        // (after the state loads have been issued: the copy's own load -> store round trip then runs beside theirs
+        // instead of ahead of them -- 12 % of the stall samples when it came first)
+        fill_rcp_table(s_rcp, threadIdx.x, (NW + 1) * 32);
         int spawn = -1;
         if constexpr (!IS_RESET) {
             bool need[IPW];
@@ -418,6 +426,7 @@ __global__ void __maxnreg__(MAXREG) traffic_step_kernel(const TArgs a) {
             listed = (int)a.st.misc[un + e32];
             total_reward = a.st.total_reward[env];
         }
+        fill_rcp_table(s_rcp, threadIdx.x, (NW + 1) * 32);
         if constexpr (!IS_RESET) {
             const uint64_t env_id = a.p.env_id_base + (uint64_t)env;
             const uint32_t blk0 = ctr >> 2;
