@@ -22,6 +22,6 @@ for f in ('snake_n1','traffic_n1','traffic_n1_1m_envs','builder_n1','climate_n1'
     for k,v in d.get('secondary',{}).items(): print('   secondary', k, round(v['value']/1e9,3), round(v['ms_per_step']*1e3,1), round(v['roofline']['frac'],3))
 PY
 CMD="python bench.py --steps 40 --warmup 5 --e2e-steps 3 --no-cpu-baseline"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_r2b.csv $CMD > $O/ncu_launches.log 2>&1; echo "launch list rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:climate_kernel -s 20 -c 1 -o $O/prof_climate_r2b python profiles/prof_step.py climate 30 > $O/ncu.log 2>&1; echo rc=$?
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/launches_r2b.csv $CMD > $O/ncu_launches.log 2>&1; echo "launch list rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:climate_step -s 20 -c 1 -o $O/prof_climate_r2b python profiles/prof_step.py climate 30 > $O/ncu.log 2>&1; echo rc=$?
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:builder_kernel -s 20 -c 1 -o $O/prof_builder_r2b python profiles/prof_step.py builder 30 > $O/ncu2.log 2>&1; echo rc=$?
