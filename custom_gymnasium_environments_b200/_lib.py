@@ -58,7 +58,7 @@ class TrafficState(C.Structure):
 
 class TrafficIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "terminated", "truncated", "reward64", "ep_return",
-                                          "ep_length", "stats")]
+                                          "ep_length", "stats", "timestep")]
 
 
 class ClimateParams(C.Structure):

@@ -467,6 +467,7 @@ __global__ void __maxnreg__(MAXREG) traffic_step_kernel(const TArgs a) {
             else if (ended) flags |= TFLAG_NEEDS_RESET;
             a.st.misc[e32] = (uint32_t)timestep | (flags << 16);
             a.st.misc[2u * un + e32] = ctr;
+            if (a.io.timestep) a.io.timestep[env] = timestep;
             if constexpr (!IS_RESET) {
                 a.io.terminated[env] = (uint8_t)term;
                 if (a.io.truncated) a.io.truncated[env] = (uint8_t)(a.p.time_limit_truncation && term);  // raw class: 0, :197

@@ -82,13 +82,14 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
             self.ep_return = z(n, dt=torch.float64)
             self.ep_length = z(n, dt=torch.int32)
             self.stats = z(3, dt=torch.float64)
+            self.timestep = z(n, dt=torch.int32)  # info["timestep"], written by the kernel (no per-step host-side op)
             self._actions = z(n, ni, dt=torch.int64)
         self._state = _lib.TrafficState(self._light.data_ptr(), self._passed.data_ptr(), self._waiting.data_ptr(),
                                         self._qmeta.data_ptr(), self._qwait.data_ptr(), self._misc.data_ptr(),
                                         self._total_reward.data_ptr())
         self._io = _lib.TrafficIO(self.obs.data_ptr(), self.reward.data_ptr(), self.terminated.data_ptr(),
                                   self.truncated.data_ptr(), self.reward64.data_ptr(), self.ep_return.data_ptr(),
-                                  self.ep_length.data_ptr(), self.stats.data_ptr())
+                                  self.ep_length.data_ptr(), self.stats.data_ptr(), self.timestep.data_ptr())
         self._infos_cache = None
         self._host = None
         self._needs_first_reset = True
@@ -149,13 +150,12 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
                 "average_queue_length": queued / ni, "throughput": passed / ni}
 
     def _infos(self):
+        # every value is a tensor the kernel writes in place: building the dict launches nothing
         if self._infos_cache is None:
             self._infos_cache = {"total_reward": self._total_reward, "reward64": self.reward64,
-                                 "episode": {"r": self.ep_return, "l": self.ep_length}, "_episode": self.terminated}
-        info = dict(self._infos_cache)
-        info["timestep"] = self._misc[0] & 0xFFFF  # (the upper bits of the word are flags)
-        info["num_vehicles"] = self._misc[1]
-        return info
+                                 "episode": {"r": self.ep_return, "l": self.ep_length}, "_episode": self.terminated,
+                                 "timestep": self.timestep, "num_vehicles": self._misc[1]}
+        return dict(self._infos_cache)
 
     # ------------------------------------------------------------------ VectorEnv API
     def reset(self, *, seed=None, options=None):

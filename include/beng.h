@@ -278,6 +278,7 @@ typedef struct beng_traffic_io {
     double *ep_return;     /* [n] nullable  written when an episode ends (auto-reset modes) */
     int32_t *ep_length;    /* [n] nullable */
     double *stats;         /* [3] nullable  running {n_episodes, sum_return, sum_length} */
+    int32_t *timestep;     /* [n] nullable  info["timestep"] (environment.py:200): current_timestep after the call, 0 after a reset */
 } beng_traffic_io;
 
 /* TrafficManagementEnv.reset (environment.py:141-166) for envs with mask[i] != 0 (NULL = all); first_call != 0 also

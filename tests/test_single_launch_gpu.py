@@ -1,0 +1,48 @@
+"""Every Batched*Env.step() with device-resident, aligned actions is exactly ONE kernel launch: no host-side tensor op
+(mask, cast, copy) rides along inside the step, so the device-timed figures of bench.py are the step kernel's."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import custom_gymnasium_environments_b200 as p
+    return p
+
+
+def make(pkg, name, n):
+    g = torch.Generator(device=DEV).manual_seed(3)
+    if name == "snake":
+        return pkg.BatchedSnakeEnv(n, device=DEV), torch.randint(0, 4, (n,), device=DEV, generator=g)
+    if name == "crypto":
+        return pkg.BatchedCryptoTradingEnv(n, None, "discrete", device=DEV), torch.randint(0, 5, (n,), device=DEV, generator=g)
+    if name == "traffic":
+        return pkg.BatchedTrafficManagementEnv(n, device=DEV), torch.randint(0, 3, (n, 9), device=DEV, generator=g)
+    if name == "builder":
+        return pkg.BatchedWorldBuilderEnv(n, device=DEV), torch.randint(0, 5, (n,), device=DEV, generator=g)
+    return pkg.BatchedSmartClimateEnv(n, device=DEV), {
+        "ac_temp": torch.rand(n, device=DEV, generator=g) * 16 + 16,
+        "lights": torch.randint(0, 2, (n, 4), device=DEV, generator=g).to(torch.int8)}
+
+
+@pytest.mark.parametrize("name", ["snake", "crypto", "traffic", "climate", "builder"])
+def test_step_is_one_kernel(pkg, name):
+    env, act = make(pkg, name, 8192)
+    env.reset()
+    lib = pkg._lib.load()
+    for _ in range(3):
+        env.step(act)
+    torch.cuda.synchronize()
+    with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+        before = lib.beng_launch_count()
+        for _ in range(5):
+            env.step(act)
+        torch.cuda.synchronize()
+    assert lib.beng_launch_count() - before == 5
+    kernels = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    assert len(kernels) == 5 and len(set(kernels)) == 1, kernels

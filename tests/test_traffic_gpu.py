@@ -45,6 +45,7 @@ def meta(g, name):
 
 def assert_state(env, st, t):
     assert np.array_equal(np_(env.current_timestep), st["timestep"]), t
+    assert np.array_equal(np_(env.timestep), st["timestep"]), t  # info["timestep"], written by the kernel itself
     assert np.array_equal(np_(env.num_vehicles), st["num_vehicles"]), t
     assert np.array_equal(np_(env.rng_counter), st["rng_counter"].astype(np.int64)), t
     assert np.array_equal(np_(env.light_phase), st["phase"]) and np.array_equal(np_(env.vehicles_passed), st["passed"])
@@ -183,3 +184,21 @@ def test_single_env_facade(pkg, tgold):
         assert [s["vehicles_passed"] for s in st] == g[f"{name}/passed"][0, t].tolist()
         assert set(info["metrics"]) == {"total_vehicles_passed", "total_waiting_time", "average_waiting_time",
                                         "total_queue_length", "average_queue_length", "throughput"}
+
+
+def test_infos_are_views_the_kernel_writes(pkg):
+    """The infos dict is made of tensors the kernel writes in place (a masked `info["timestep"]` used to cost an extra
+    elementwise launch per step inside the timed region; tests/test_single_launch_gpu.py counts the launches)."""
+    n = 4096
+    env = pkg.BatchedTrafficManagementEnv(n, device=DEV, seed=5, autoreset_mode="next_step", max_timesteps=7)
+    env.reset()
+    actions = torch.randint(0, 3, (n, env.num_intersections), device=DEV)
+    lib = pkg._lib.load()
+    for t in range(20):
+        before = lib.beng_launch_count()
+        _, _, _, _, infos = env.step(actions)
+        assert lib.beng_launch_count() - before == 1
+        assert infos["timestep"].data_ptr() == env.timestep.data_ptr()
+        assert torch.equal(infos["timestep"], env.current_timestep.to(torch.int32))
+        assert torch.equal(infos["num_vehicles"], env.num_vehicles)
+
