@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Dict, Discrete, batch_space
-from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, as_device_actions, host_source, require_cuda, stream_ptr
 
 BUILDING_NAMES = ("farm", "lumberyard", "quarry", "house")
 BUILDER_STAT_NAMES = ("n_episodes", "sum_return", "sum_length", "wins")
@@ -163,12 +163,11 @@ class BatchedWorldBuilderEnv(_VectorEnvBase):
                           "terminated": torch.zeros(n, dtype=torch.bool, **pin)}
         h = self._host
         src = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
-        if src.data_ptr() != h["actions"].data_ptr():
-            h["actions"].copy_(src.reshape(self.num_envs))
+        src = self._host_src = host_source(src, h["actions"])
         with torch.cuda.device(self.device):
             rc = self.lib.beng_builder_step_host(
                 C.byref(self.params), C.byref(self._state), self._actions.data_ptr(), C.byref(self._io),
-                self.num_envs, h["actions"].data_ptr(), h["grid"].data_ptr() if copy_obs else None,
+                self.num_envs, src.data_ptr(), h["grid"].data_ptr() if copy_obs else None,
                 h["resources"].data_ptr(), h["capacity"].data_ptr(), h["win_steps"].data_ptr(),
                 h["reward"].data_ptr(), h["terminated"].data_ptr(), stream_ptr(self.device))
             _lib.check(rc, "beng_builder_step_host")

@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Dict, MultiBinary, batch_space
-from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, host_source, require_cuda, stream_ptr
 
 OBS_DIM = 9
 CLIMATE_STAT_NAMES = ("n_episodes", "sum_return", "sum_length")
@@ -166,14 +166,13 @@ class BatchedSmartClimateEnv(_VectorEnvBase):
         ac, lights = self._split_action(actions)
         ac_src = ac if isinstance(ac, torch.Tensor) else torch.as_tensor(np.asarray(ac, dtype=np.float32))
         li_src = lights if isinstance(lights, torch.Tensor) else torch.as_tensor(np.asarray(lights, dtype=np.int8))
-        if ac_src.data_ptr() != h["ac"].data_ptr():
-            h["ac"].copy_(ac_src.reshape(-1))
-        if li_src.data_ptr() != h["lights"].data_ptr():
-            h["lights"].copy_(li_src.reshape(-1, 4))
+        ac_src = host_source(ac_src, h["ac"])
+        li_src = host_source(li_src, h["lights"])
+        self._host_src = (ac_src, li_src)
         with torch.cuda.device(self.device):
             rc = self.lib.beng_climate_step_host(
                 C.byref(self.params), C.byref(self._state), self._ac.data_ptr(), self._lights.data_ptr(),
-                C.byref(self._io), self.num_envs, h["ac"].data_ptr(), h["lights"].data_ptr(),
+                C.byref(self._io), self.num_envs, ac_src.data_ptr(), li_src.data_ptr(),
                 h["obs"].data_ptr() if copy_obs else None, h["reward"].data_ptr(), h["terminated"].data_ptr(),
                 h["truncated"].data_ptr(), stream_ptr(self.device))
             _lib.check(rc, "beng_climate_step_host")

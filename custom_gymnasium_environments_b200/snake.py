@@ -18,7 +18,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, Discrete, batch_space
-from .vector import _EnvBase, AUTORESET_MODES, LazyInfos, _VectorEnvBase, _mode_name, as_device_actions, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, LazyInfos, _VectorEnvBase, _mode_name, as_device_actions, host_source, require_cuda, stream_ptr
 
 STAT_NAMES = ("n_episodes", "sum_return", "sum_length", "sum_score", "max_score")
 
@@ -218,12 +218,11 @@ class BatchedSnakeEnv(_VectorEnvBase):
             raise RuntimeError("call reset() before step()")
         h = self._host_buffers()
         src = torch.as_tensor(np.asarray(actions) if not isinstance(actions, torch.Tensor) else actions)
-        if src.data_ptr() != h["actions"].data_ptr():
-            h["actions"].copy_(src.reshape(self.num_envs))
+        src = self._host_src = host_source(src, h["actions"])
         with torch.cuda.device(self.device):
             rc = self.lib.beng_snake_step_host(
                 C.byref(self.params), C.byref(self._state), self._actions.data_ptr(), C.byref(self._next_io(True)),
-                self.num_envs, h["actions"].data_ptr(), h["obs"].data_ptr() if copy_obs else None,
+                self.num_envs, src.data_ptr(), h["obs"].data_ptr() if copy_obs else None,
                 h["reward"].data_ptr(), h["terminated"].data_ptr(), h["truncated"].data_ptr(),
                 h["score"].data_ptr(), h["snake_length"].data_ptr(), stream_ptr(self.device))
             _lib.check(rc, "beng_snake_step_host")

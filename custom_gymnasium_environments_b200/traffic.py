@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .spaces import Box, MultiDiscrete, batch_space
-from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, require_cuda, stream_ptr
+from .vector import _EnvBase, AUTORESET_MODES, _VectorEnvBase, _mode_name, host_source, require_cuda, stream_ptr
 
 # config.py:6-12,23
 DEFAULT_GRID_SIZE = (5, 5)
@@ -221,12 +221,11 @@ class BatchedTrafficManagementEnv(_VectorEnvBase):
                           "truncated": torch.zeros(n, dtype=torch.bool, **pin)}
         h = self._host
         src = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
-        if src.data_ptr() != h["actions"].data_ptr():
-            h["actions"].copy_(src.reshape(h["actions"].shape))
+        src = self._host_src = host_source(src, h["actions"])
         with torch.cuda.device(self.device):
             rc = self.lib.beng_traffic_step_host(
                 C.byref(self.params), C.byref(self._state), self._actions.data_ptr(), C.byref(self._io),
-                self.num_envs, h["actions"].data_ptr(), h["obs"].data_ptr() if copy_obs else None,
+                self.num_envs, src.data_ptr(), h["obs"].data_ptr() if copy_obs else None,
                 h["reward"].data_ptr(), h["terminated"].data_ptr(), h["truncated"].data_ptr(),
                 stream_ptr(self.device))
             _lib.check(rc, "beng_traffic_step_host")

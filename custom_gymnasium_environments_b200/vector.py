@@ -69,6 +69,19 @@ def as_device_actions(actions, buf: torch.Tensor) -> torch.Tensor:
     return buf
 
 
+def host_source(src: "torch.Tensor", staging: "torch.Tensor") -> "torch.Tensor":
+    """The pinned host tensor a step_host() call uploads its actions from: the caller's own tensor when it already is
+    pinned, contiguous and of the staging buffer's dtype and size (no host-to-host copy inside the call), otherwise the
+    env's pinned staging buffer after copying into it.  The upload is asynchronous: with sync=False the caller must keep
+    the tensor alive and unchanged until the stream has consumed it."""
+    if src.device.type == "cpu" and src.dtype == staging.dtype and src.numel() == staging.numel() \
+            and src.is_contiguous() and src.is_pinned():
+        return src
+    if src.data_ptr() != staging.data_ptr():
+        staging.copy_(src.reshape(staging.shape))
+    return staging
+
+
 class LazyInfos(dict):
     """infos dict whose derived entries are computed on access (no per-step kernels or HBM writes for values
     nobody reads).  `lazy[key]` is a zero-argument callable returning the tensor."""

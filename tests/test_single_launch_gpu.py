@@ -46,3 +46,34 @@ def test_step_is_one_kernel(pkg, name):
     assert lib.beng_launch_count() - before == 5
     kernels = [e.name for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     assert len(kernels) == 5 and len(set(kernels)) == 1, kernels
+
+
+@pytest.mark.parametrize("name", ["snake", "crypto", "traffic", "climate", "builder"])
+def test_step_host_from_pinned_tensors_matches_numpy(pkg, name):
+    """step_host() uploads straight from a caller's pinned tensor (no staging copy); same results as the numpy path."""
+    import numpy as np
+
+    n = 2048 + 5
+    env_a, act = make(pkg, name, n)
+    env_b, _ = make(pkg, name, n)
+    env_a.reset(); env_b.reset()
+    for t in range(6):
+        if isinstance(act, dict):
+            dev = {k: (v + t) % 2 if v.dtype == torch.int8 else v for k, v in act.items()}
+            host_np = {k: v.cpu().numpy() for k, v in dev.items()}
+            host_pin = {k: v.cpu().pin_memory() for k, v in dev.items()}
+        else:
+            dev = (act + t) % (int(act.max()) + 1)
+            host_np, host_pin = dev.cpu().numpy(), dev.cpu().pin_memory()
+        out_a = env_a.step_host(host_np)
+        out_b = env_b.step_host(host_pin)
+        used = env_b._host_src
+        pins = list(host_pin.values()) if isinstance(host_pin, dict) else [host_pin]
+        used = list(used) if isinstance(used, tuple) else [used]
+        assert {u.data_ptr() for u in used} == {p.data_ptr() for p in pins}  # no staging copy
+        for x, y in zip(out_a[:4], out_b[:4]):
+            if isinstance(x, dict):
+                for k in x:
+                    assert np.array_equal(np.asarray(x[k]), np.asarray(y[k])), (name, t, k)
+            else:
+                assert np.array_equal(np.asarray(x), np.asarray(y)), (name, t)
