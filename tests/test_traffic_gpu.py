@@ -135,8 +135,12 @@ def test_sharding_host_path_masked_reset_state_dict(pkg):
     from custom_gymnasium_environments_b200.dist import shard_range
 
     n, T, seed = 3000, 80, 4
+    from oracle.c_oracle import TrafficOracle
+
     whole = pkg.BatchedTrafficManagementEnv(n, device=DEV, seed=seed)
     host = pkg.BatchedTrafficManagementEnv(n, device=DEV, seed=seed)
+    orc = TrafficOracle(n, seed=seed)
+    orc.reset()
     shards = []
     for r in range(3):
         s, c = shard_range(n, r, 3)
@@ -148,6 +152,7 @@ def test_sharding_host_path_masked_reset_state_dict(pkg):
     for t in range(T):
         a = torch.randint(0, 3, (n, 9), device=DEV, generator=gen)
         whole.step(a)
+        orc.step(np_(a), want_obs=False)
         obs, rew, term, trunc, _ = host.step_host(np_(a))
         assert isinstance(obs, np.ndarray) and np.array_equal(obs, np_(whole.obs)) and np.array_equal(rew, np_(whole.reward))
         for s, c, e in shards:
@@ -155,9 +160,18 @@ def test_sharding_host_path_masked_reset_state_dict(pkg):
             assert torch.equal(e.obs, whole.obs[s:s + c]) and torch.equal(e.reward64, whole.reward64[s:s + c])
     mask = torch.zeros(n, dtype=torch.bool, device=DEV)
     mask[::2] = True
-    whole.reset(options={"reset_mask": mask})
-    assert bool((whole.current_timestep[::2] == 0).all()) and bool((whole.current_timestep[1::2] == T).all())
-    assert bool((whole.num_vehicles[::2] == 0).all()) and bool((whole.num_vehicles[1::2] > 0).any())
+    obs_after, _ = whole.reset(options={"reset_mask": mask})
+    # the masked reset against the oracle's: selected envs are fresh (every state word, observation of a fresh env),
+    # the others untouched, and both continue identically
+    assert np.array_equal(np_(obs_after), orc.reset(np_(mask)))
+    assert_state(whole, orc.state(), "masked reset")
+    a = torch.randint(0, 3, (n, 9), device=DEV, generator=gen)
+    whole.step(a)
+    orc.step(np_(a))
+    assert np.array_equal(np_(whole.obs), orc.obs) and np.array_equal(np_(whole.reward64), orc.reward64)
+    assert_state(whole, orc.state(), "step after masked reset")
+    assert bool((whole.current_timestep[::2] == 1).all()) and bool((whole.current_timestep[1::2] == T + 1).all())
+    assert bool((whole.num_vehicles[::2] <= 1).all()) and bool((whole.num_vehicles[1::2] > 1).any())
     clone = pkg.BatchedTrafficManagementEnv(n, device=DEV, seed=77)
     clone.load_state_dict(whole.state_dict())
     a = torch.randint(0, 3, (n, 9), device=DEV, generator=gen)
