@@ -51,6 +51,32 @@ struct EnvStream {
         // select without dynamic register indexing
         return lane == 0 ? cache.v[0] : lane == 1 ? cache.v[1] : lane == 2 ? cache.v[2] : cache.v[3];
     }
+    // The next N <= 9 draws at once, for callers that know how many they will consume (a fixed-shape step): the two or
+    // three blocks they span are computed up front and each draw is one 4-way select on the starting offset, instead
+    // of a block check, an offset select and a counter update per draw.  Same values as N calls of u32().
+    template <int N>
+    __device__ __forceinline__ void take(uint32_t (&out)[N]) {
+        static_assert(N >= 1 && N <= 9, "at most three blocks");
+        const uint32_t blk = ctr >> 2, o = ctr & 3u;
+        const Philox4 A = philox4x32_10(blk, env_lo, env_hi, stream, k0, k1);
+        Philox4 B = A, C = A;
+        if (N > 1) B = philox4x32_10(blk + 1, env_lo, env_hi, stream, k0, k1);
+        if (N > 5 && o + N > 8) C = philox4x32_10(blk + 2, env_lo, env_hi, stream, k0, k1);
+        const uint32_t v[12] = {A.v[0], A.v[1], A.v[2], A.v[3], B.v[0], B.v[1], B.v[2], B.v[3], C.v[0], C.v[1], C.v[2], C.v[3]};
+#pragma unroll
+        for (int j = 0; j < N; ++j) out[j] = o == 0 ? v[j] : o == 1 ? v[j + 1] : o == 2 ? v[j + 2] : v[j + 3];
+        ctr += N;
+        cached_blk = 0xFFFFFFFFu;  // (the lazy cache is not kept in step with this path)
+    }
+    // random(): 53 bits from two given draws (the construction of random53())
+    static __device__ __forceinline__ double to_random53(uint32_t d0, uint32_t d1) {
+        return ((double)(d0 >> 5) * 67108864.0 + (double)(d1 >> 6)) * (1.0 / 9007199254740992.0);
+    }
+    // normal(mu, sd) from four given draws (the construction of normal())
+    static __device__ __forceinline__ double to_normal(double mu, double sd, uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3) {
+        const double u1 = to_random53(d0, d1), u2 = to_random53(d2, d3);
+        return mu + sd * (sqrt(-2.0 * log(1.0 - u1)) * cos(2.0 * 3.141592653589793 * u2));
+    }
     // randint(a, b) inclusive: one draw, multiply-high range map
     __device__ __forceinline__ int randint(int a, int b) { return a + (int)__umulhi(u32(), (uint32_t)(b - a + 1)); }
     // random(): two draws, 53 bits, same construction as CPython's random.random()

@@ -35,10 +35,10 @@ struct KArgs {
 __device__ __forceinline__ double kclip(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // get_outside_temp, utils.py:5-13
-__device__ __forceinline__ double outside_temp(double tod, EnvStream &rng) {
-    const double base = (0 <= tod && tod < 8) ? 25.0 : ((8 <= tod && tod < 16) ? 45.0 : 35.0);
-    return rng.normal(base, 5.0);
+__device__ __forceinline__ double outside_base(double tod) {
+    return (0 <= tod && tod < 8) ? 25.0 : ((8 <= tod && tod < 16) ? 45.0 : 35.0);
 }
+__device__ __forceinline__ double outside_temp(double tod, EnvStream &rng) { return rng.normal(outside_base(tod), 5.0); }
 
 // One env's state and action words as loaded (requested together, before anything is inspected).
 struct KIn {
@@ -119,10 +119,13 @@ __device__ __forceinline__ void step_env(const KArgs &a, long long env, const KI
             }
             step = min(step + 1, 65535);
             const double tod = div_const<60>((double)(step % 1440));  // :91, (step % 1440) / 60 correctly rounded
-            outside = outside_temp(tod, rng);
+            // the step's six draws (normal: four, choice: two) in one go
+            uint32_t dr[6];
+            rng.take(dr);
+            outside = EnvStream::to_normal(outside_base(tod), 5.0, dr[0], dr[1], dr[2], dr[3]);  // get_outside_temp
             {   // update_occupancy, utils.py:15-22: rng.choice(values, p) == inverse-CDF lookup
                 const bool day = (9 <= tod && tod < 18);
-                const double u = rng.random53();
+                const double u = EnvStream::to_random53(dr[4], dr[5]);
                 const double c0 = day ? 0x1.999999999999ap-4 : 0x1.9999999999998p-3;
                 const double c1 = day ? 0x1.999999999999ap-2 : 0x1.3333333333333p-1;
                 const double c2 = day ? 0x1.999999999999ap-1 : 0x1.cccccccccccccp-1;
