@@ -527,6 +527,34 @@ def bench_env(ctx, env_name, n, steps, warmup, e2e_steps):
     value = n * world * steps / (ms_max * 1e-3)
     value_warm = n * world * steps / (ms_warm * 1e-3)
 
+    # ---- launch-bound size (traffic at 65,536 envs: ~12 us of L2-warm kernel per ~13 us of Python enqueue): the same
+    # back-to-back loop replayed from ONE CUDA graph, per GPU, this rank's own figure (no collective: a rank whose capture
+    # failed reports None).  step() is a pure stream operation (tests/test_single_launch_gpu.py), so the capture is
+    # just the loop.
+    graph_warm = None
+    if env_name == "traffic" and flush:
+        try:
+            k_graph = min(32, pool)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(graph):
+                for t in range(k_graph):
+                    env.step(tapes[t])
+            reps = max(2, steps // k_graph)
+            graph.replay()
+            torch.cuda.synchronize(dev)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            for _ in range(reps):
+                graph.replay()
+            g1.record(stream)
+            torch.cuda.synchronize(dev)
+            us = g0.elapsed_time(g1) * 1e3 / (reps * k_graph)
+            graph_warm = {"env_steps_per_sec_per_gpu": n / (us * 1e-6), "us_per_step": us, "steps_per_graph": k_graph,
+                          "note": "L2-warm back-to-back steps replayed from one CUDA graph (rank 0's GPU)"}
+        except Exception as ex:  # noqa: BLE001 -- a diagnostic extra, never the headline
+            graph_warm = {"error": str(ex)[:200]}
+
     # ---- end-to-end through the host-buffer C-ABI call -------------------------------------------
     e2e_steps = max(1, min(steps, e2e_steps))
     host_tapes = [to_host(tapes[t % pool]) for t in range(min(e2e_steps + 2, 8))]
@@ -610,6 +638,7 @@ def bench_env(ctx, env_name, n, steps, warmup, e2e_steps):
         "gpu_launches": int(launches),
         "l2_flushed_between_steps": bool(flush),
         "value_l2_warm": value_warm if flush else None,
+        "l2_warm_cuda_graph": graph_warm,
         "clocks": sampler.summary(),
         "episodes": summary,
     }
